@@ -85,7 +85,7 @@ def test_dqn_step_matches_reference(key):
     np.testing.assert_allclose(pd[:, 2], g[key + '_param_digest'][:, 2], rtol=ptol)
     np.testing.assert_allclose(pd[:, 3:], g[key + '_param_digest'][:, 3:], rtol=1e-3, atol=20 * ptol)
     md = np.stack([O.digest(mom[n]) for n in names])
-    np.testing.assert_allclose(md[:, 2], g[key + '_mom_digest'][:, 2], rtol=5e-3, atol=1e-7)
+    np.testing.assert_allclose(md[:, 2], g[key + '_mom_digest'][:, 2], rtol=5e-3 if nsteps == 1 else 3e-2, atol=1e-7)
     bn = np.concatenate([pol[n].numpy().ravel() for n, _, k in O.state_spec(C, A) if k == 'buffer'])
     np.testing.assert_allclose(bn, g[key + '_bn'], rtol=1e-3, atol=1e-4)
     nbt = [int(pol[n]) for n, _, k in O.state_spec(C, A) if k == 'nbt']
