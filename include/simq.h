@@ -1,0 +1,120 @@
+/* simq — C-ABI of the B200-native DQN Q-map path (spatial-action-map Q-network).
+ *
+ * The reference (jimmyyhwu/spatial-intention-maps @ 336e03a) has no FFI: its boundary for this path
+ * is the Python duck-type surface of networks.FCN / train.train.  Each entry point
+ * below replaces one piece of that surface; the Python host side
+ * (spatial_intention_maps_b200/{networks,train,policies}.py) binds them with ctypes and mirrors
+ * the reference names.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, nonzero on error (message: simq_last_error(),
+ * thread-local).  No exceptions, no ownership transfer: all tensors are caller-owned DEVICE
+ * pointers that must stay valid until `stream` has executed the call's work.  The library owns
+ * only the ctx workspace.  A ctx is bound to one device and is not thread-safe.
+ *
+ * Flat parameter vector ("params"/"grads"/"momentum"): the 70 trainable tensors of networks.FCN in
+ * reference state_dict order (networks.py:7-14, resnet.py:52-68; resnet18.fc.* excluded — it never
+ * runs, resnet.py:93-104), each in PyTorch's native layout (OIHW for conv weights), fp32,
+ * concatenated.  "bn" = for each of the 22 BatchNorm2d in the same order: running_mean[ch] then
+ * running_var[ch], fp32.  "nbt" = 22 x int64 num_batches_tracked.  simq_layout() reports offsets.
+ */
+#ifndef SIMQ_H_
+#define SIMQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct simq_ctx simq_ctx;
+typedef void* simq_stream;            /* cudaStream_t */
+
+#define SIMQ_N_BN 22
+#define SIMQ_MAP 96                   /* envs.py:2010 state width */
+
+/* conv back-end: the tcgen05/TMA kernels are the product; the FMA kernels are an on-device
+ * fp32 comparator for tests/debug (never the default). */
+enum { SIMQ_BACKEND_UMMA = 0, SIMQ_BACKEND_FMA = 1 };
+/* x layouts accepted by the stem */
+enum { SIMQ_X_NCHW = 0, SIMQ_X_NHWC = 1 };
+
+const char* simq_last_error(void);
+int simq_version(void);
+
+/* Sizes/offsets of the flat vectors for FCN(C, A).  Any out pointer may be NULL.
+ * param_offsets: 71 entries (70 tensors + end), bn_offsets: 23 entries (22 BNs + end; each BN holds
+ * 2*ch floats). */
+int simq_layout(int C, int A, int64_t* n_params, int64_t* n_bn, int64_t* param_offsets, int64_t* bn_offsets);
+
+/* Replaces DQNPolicy.build_policy_nets' per-net device state (policies.py:35-42). */
+int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch);
+void simq_ctx_destroy(simq_ctx*);
+int simq_set_backend(simq_ctx*, int backend);
+size_t simq_workspace_bytes(const simq_ctx*);
+
+/* Replaces FCN.forward (networks.py:16-26).  x: f32 [B,C,96,96] (NCHW) or [B,96,96,C] (NHWC);
+ * q: f32 [B,A,96,96].  training!=0: batch-statistics BN, updates bn/nbt in place (also under
+ * no_grad, like nn.BatchNorm2d).  save_for_backward!=0 keeps activations in the ctx for ONE
+ * following simq_fcn_backward.  Weights are re-packed from `params` on every call unless
+ * params_version equals the version of the previous call with the same pointer (0 = always). */
+int simq_fcn_forward(simq_ctx*, const float* params, float* bn, int64_t* nbt, const float* x, int B,
+                     int x_layout, int training, int save_for_backward, float* q, uint64_t params_version,
+                     simq_stream stream);
+
+/* Replaces loss.backward() through the FCN (train.py:132).  dq: f32 [B,A,96,96] dense gradient of
+ * the loss w.r.t. the Q-map.  grads (flat, same layout as params) is OVERWRITTEN.  x must be the
+ * tensor passed to the saving forward. */
+int simq_fcn_backward(simq_ctx*, const float* params, const float* x, int x_layout, const float* dq, int B,
+                      float* grads, simq_stream stream);
+
+/* Replaces train.py:115-129: gather Q(s,a), Double-DQN target, SmoothL1, td_error, dL/dQ.
+ * q_s [B,A,96,96]; q_next_online/q_next_target [Bn,A,96,96] rows = non-terminal samples in order;
+ * nonfinal[B] in {0,1}; out2[0]=loss, out2[1]=mean|td|; dq (may be NULL) [B,A,96,96] is zero-filled
+ * and receives the one-hot gradient. double_dqn==0 -> train.py:124. */
+int simq_dqn_tail(simq_ctx*, const float* q_s, const float* q_next_online, const float* q_next_target,
+                  const int64_t* action, const float* reward, const uint8_t* nonfinal, float gamma,
+                  int B, int Bn, int double_dqn, float* out2, float* dq, simq_stream stream);
+
+/* Replaces clip_grad_norm_ + SGD.step (train.py:133-135, ctor :186) over the flat vectors.
+ * first_step!=0: momentum := g (torch.optim.SGD first-step rule).  clip_norm<=0: no clipping.
+ * grad_norm_out (device float, may be NULL) receives the pre-clip global L2 norm. */
+int simq_sgd_step(simq_ctx*, float* params, float* grads, float* momentum, float lr, float mom, float wd,
+                  float clip_norm, int first_step, float* grad_norm_out, simq_stream stream);
+
+/* Replaces the whole of train.train (train.py:108-141) on device-resident inputs: online forward
+ * on s (saving), online train-mode forward on s' (argmax), target eval forward on s', tail,
+ * backward, clip, SGD.  out2 as in simq_dqn_tail.  apply_update==0 stops after the gradients
+ * (data-parallel callers all-reduce `grads`, then call simq_sgd_step).  target_version: as params_version of
+ * simq_fcn_forward, for the target network's packed weights (it changes only at target syncs). */
+int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const float* target_params,
+                    const float* target_bn, uint64_t target_version, float* grads, float* momentum,
+                    const float* s, const float* s_next, int x_layout, const int64_t* action,
+                    const float* reward, const uint8_t* nonfinal, int B, int Bn, float gamma, float lr,
+                    float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
+                    float* out2, simq_stream stream);
+
+/* Replaces the greedy branch of DQNPolicy.step (policies.py:56-64): eval forward at batch B and
+ * per-sample flat first-max argmax.  action_out: int64[B]; q (may be NULL) full Q-maps. */
+int simq_greedy_action(simq_ctx*, const float* params, const float* bn, const float* x, int B, int x_layout,
+                       int64_t* action_out, float* q, uint64_t params_version, simq_stream stream);
+
+/* How many of this library's kernels were launched through this ctx so far. */
+int64_t simq_launch_count(const simq_ctx*);
+
+/* ---- test hooks (exercise single kernels through the C-ABI; used by tests/ only) ---- */
+/* Copy an internal activation of the last forward (set 0 = saved set, 1 = scratch set) as dense
+ * NCHW f32.  id: see simq_debug_tensor_name(). Returns channels*H*W per sample through *chw. */
+int simq_debug_get(simq_ctx*, int set, int id, int B, float* out_nchw, int64_t* chw, simq_stream stream);
+const char* simq_debug_tensor_name(int id);
+/* Shifted-GEMM convolution on the pitch-25 layout with either back-end.
+ * a: f32 NCHW [B,Cin,24,24]; w: f32 OIHW [Cout,Cin,k,k] (k=1|3); mode 0 = forward conv (out
+ * [B,Cout,24,24]), 1 = dgrad (a is dY [B,Cout,24,24], out is dX [B,Cin,24,24]),
+ * 2 = wgrad (a = X [B,Cin,24,24], a2 = dY [B,Cout,24,24], out = dW OIHW). */
+int simq_test_conv(simq_ctx*, int backend, int mode, int B, int Cin, int Cout, int k, const float* a,
+                   const float* a2, const float* w, float* out, simq_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMQ_H_ */

@@ -163,6 +163,45 @@ def forward(st, x: torch.Tensor, training: bool) -> torch.Tensor:
     return F.conv2d(x, st['conv3.weight'], st['conv3.bias'])          # :26
 
 
+def forward_trace(st, x: torch.Tensor, training: bool) -> Dict[str, torch.Tensor]:
+    """Same arithmetic as :func:`forward`, returning the named intermediates the CUDA library can
+    export through ``simq_debug_get`` (tests localise a mismatch to one layer with it).  Conv outputs
+    of the head are recorded WITHOUT their bias (the library folds the bias into the BN shift)."""
+    tr: Dict[str, torch.Tensor] = {}
+    h = F.conv2d(x, st['resnet18.conv1.weight'], None, 2, 3)
+    tr['raw0'] = h
+    h = F.max_pool2d(F.relu(_bn(st, 'resnet18.bn1', h, training)), 3, 2, 1)
+    tr['a0'] = h
+    b = 0
+    for li in range(1, 5):
+        for blk in range(2):
+            p = f'resnet18.layer{li}.{blk}'
+            r1 = F.conv2d(h, st[p + '.conv1.weight'], None, 1, 1)
+            b1 = F.relu(_bn(st, p + '.bn1', r1, training))
+            r2 = F.conv2d(b1, st[p + '.conv2.weight'], None, 1, 1)
+            o = _bn(st, p + '.bn2', r2, training)
+            ident = h
+            if (p + '.downsample.0.weight') in st:
+                rd = F.conv2d(h, st[p + '.downsample.0.weight'])
+                tr[f'blk{b}.rawd'] = rd
+                ident = _bn(st, p + '.downsample.1', rd, training)
+            h = F.relu(o + ident)
+            tr[f'blk{b}.raw1'], tr[f'blk{b}.b1'], tr[f'blk{b}.raw2'], tr[f'blk{b}.out'] = r1, b1, r2, h
+            b += 1
+    r = F.conv2d(h, st['conv1.weight'], None)
+    tr['raw_h1'] = r
+    h = F.relu(_bn(st, 'bn1', r + st['conv1.bias'].view(1, -1, 1, 1), training))
+    h = F.interpolate(h, scale_factor=2, mode='bilinear', align_corners=True)
+    tr['u1'] = h
+    r = F.conv2d(h, st['conv2.weight'], None)
+    tr['raw_h2'] = r
+    h = F.relu(_bn(st, 'bn2', r + st['conv2.bias'].view(1, -1, 1, 1), training))
+    tr['t'] = F.conv2d(h, st['conv3.weight'], None)
+    h = F.interpolate(h, scale_factor=2, mode='bilinear', align_corners=True)
+    tr['q'] = F.conv2d(h, st['conv3.weight'], st['conv3.bias'])
+    return tr
+
+
 def hwc_to_nchw(states: Sequence[np.ndarray]) -> torch.Tensor:
     """policies.py:44-45 (ToTensor on float32 HWC ndarray = transpose only, no /255) + train.py:109 cat."""
     return torch.from_numpy(np.ascontiguousarray(np.stack(states).transpose(0, 3, 1, 2)))

@@ -1,0 +1,604 @@
+// C-ABI of the simq library (include/simq.h): context, layouts, and the orchestration of the
+// forward / backward / tail / optimiser kernels for networks.FCN (reference networks.py:6-26,
+// resnet.py:50-120) and train.train (train.py:108-141).
+#include "../../include/simq.h"
+#include "kernels.h"
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+long long g_simq_launches = 0;
+static thread_local char g_err[512] = "";
+
+void simq_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* simq_last_error(void) { return g_err; }
+extern "C" int simq_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------------
+// network description: the 70 trainable tensors / 22 BatchNorms of networks.FCN in state_dict order
+// ------------------------------------------------------------------------------------------------
+struct ConvP { int w; int cin, cout, k; };        // index of the weight in the param list
+struct BnP { int gamma; int ch; int idx; };       // index of gamma (beta = gamma + 1), BN ordinal
+struct BlockP { ConvP c1, c2, ds; BnP b1, b2, bds; bool has_ds; int cin, planes; };
+
+struct NetDesc {
+    int C, A;
+    std::vector<int64_t> poff;      // 71
+    std::vector<int64_t> bnoff;     // 23
+    ConvP stem; BnP stem_bn;
+    BlockP blk[8];
+    ConvP h1, h2, h3; int h1_bias, h2_bias, h3_bias; BnP hbn1, hbn2;
+};
+
+static void build_desc(NetDesc& d, int C, int A) {
+    d.C = C; d.A = A;
+    d.poff.clear(); d.bnoff.clear();
+    int64_t po = 0, bo = 0; int np = 0, nb = 0;
+    auto add_param = [&](int64_t n) { d.poff.push_back(po); po += n; return np++; };
+    auto add_conv = [&](int cin, int cout, int k) { ConvP c; c.cin = cin; c.cout = cout; c.k = k; c.w = add_param((int64_t)cout * cin * k * k); return c; };
+    auto add_bn = [&](int ch) { BnP b; b.ch = ch; b.gamma = add_param(ch); add_param(ch); b.idx = nb++; d.bnoff.push_back(bo); bo += 2 * ch; return b; };
+    d.stem = add_conv(C, 64, 7);
+    d.stem_bn = add_bn(64);
+    int inpl = 64;
+    const int planes_of[4] = {64, 128, 256, 512};
+    for (int li = 0; li < 4; ++li)
+        for (int b = 0; b < 2; ++b) {
+            BlockP& B = d.blk[li * 2 + b];
+            int planes = planes_of[li];
+            B.cin = b == 0 ? inpl : planes; B.planes = planes;
+            B.c1 = add_conv(B.cin, planes, 3); B.b1 = add_bn(planes);
+            B.c2 = add_conv(planes, planes, 3); B.b2 = add_bn(planes);
+            B.has_ds = (b == 0 && inpl != planes);
+            if (B.has_ds) { B.ds = add_conv(inpl, planes, 1); B.bds = add_bn(planes); }
+            if (b == 1) inpl = planes;
+        }
+    d.h1 = add_conv(512, 128, 1); d.h1_bias = add_param(128); d.hbn1 = add_bn(128);
+    d.h2 = add_conv(128, 32, 1); d.h2_bias = add_param(32); d.hbn2 = add_bn(32);
+    d.h3 = add_conv(32, A, 1); d.h3_bias = add_param(A);
+    d.poff.push_back(po); d.bnoff.push_back(bo);
+}
+
+extern "C" int simq_layout(int C, int A, int64_t* n_params, int64_t* n_bn, int64_t* param_offsets, int64_t* bn_offsets) {
+    if (C < 1 || C > 64 || A < 1 || A > 2) { simq_set_error("simq_layout: C=%d A=%d unsupported", C, A); return 1; }
+    NetDesc d; build_desc(d, C, A);
+    if (n_params) *n_params = d.poff.back();
+    if (n_bn) *n_bn = d.bnoff.back();
+    if (param_offsets) memcpy(param_offsets, d.poff.data(), sizeof(int64_t) * d.poff.size());
+    if (bn_offsets) memcpy(bn_offsets, d.bnoff.data(), sizeof(int64_t) * d.bnoff.size());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct ActSet {
+    float* raw0; Split a0;
+    struct { float *raw1, *raw2, *rawd; Split b1, out; } blk[8];
+    float* raw_h1; Split u1; float* raw_h2; float* t;
+    float* bnstat;                   // [22][4][MAX_CH] : mean, invstd, scale, shift
+    int B; int training; bool valid;
+};
+
+struct PackedSet {                   // split-bf16 shadows of the conv weights of one parameter vector
+    Split fwd[21], bwd[21];          // 16 3x3 + 3 downsample + head conv1 + head conv2, in network order
+    const float* key; uint64_t version; bool used;
+};
+
+struct simq_ctx {
+    int device, maxB, backend;
+    NetDesc d;
+    char* pool; size_t pool_bytes, pool_used;
+    ActSet set[2];
+    PackedSet packed[2]; int packed_next;
+    // scratch
+    float* partials; float* sums; double* dpartials;
+    float *G[2], *g_mid, *du1, *dt, *dz0, *dy0, *hp, *wscratch, *stem_partials;
+    Split dyA, dyB, dy2h;
+    float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
+    long long launches0;
+};
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+template <typename T>
+static T* carve(simq_ctx* c, size_t count, bool dry) {
+    size_t bytes = align256(count * sizeof(T));
+    T* p = dry ? nullptr : reinterpret_cast<T*>(c->pool + c->pool_used);
+    c->pool_used += bytes;
+    return p;
+}
+static Split carve_split(simq_ctx* c, size_t count, bool dry) {
+    Split s; s.hi = carve<bf16>(c, count, dry); s.lo = carve<bf16>(c, count, dry); return s;
+}
+
+static void conv_list(const NetDesc& d, std::vector<ConvP>& out) {
+    out.clear();
+    for (int b = 0; b < 8; ++b) { out.push_back(d.blk[b].c1); out.push_back(d.blk[b].c2); if (d.blk[b].has_ds) out.push_back(d.blk[b].ds); }
+    out.push_back(d.h1); out.push_back(d.h2);
+}
+static int conv_slot(const NetDesc& d, int w_index) {
+    std::vector<ConvP> l; conv_list(d, l);
+    for (size_t i = 0; i < l.size(); ++i) if (l[i].w == w_index) return (int)i;
+    return -1;
+}
+
+static void carve_all(simq_ctx* c, bool dry) {
+    const size_t B = c->maxB, R25 = B * IMG25, R48 = B * 2304;
+    const NetDesc& d = c->d;
+    c->pool_used = 0;
+    for (int s = 0; s < 2; ++s) {
+        ActSet& S = c->set[s];
+        S.raw0 = carve<float>(c, R48 * 64, dry);
+        S.a0 = carve_split(c, R25 * 64, dry);
+        for (int b = 0; b < 8; ++b) {
+            size_t n = R25 * d.blk[b].planes;
+            S.blk[b].raw1 = carve<float>(c, n, dry);
+            S.blk[b].raw2 = carve<float>(c, n, dry);
+            S.blk[b].rawd = d.blk[b].has_ds ? carve<float>(c, n, dry) : nullptr;
+            S.blk[b].b1 = carve_split(c, n, dry);
+            S.blk[b].out = carve_split(c, n, dry);
+        }
+        S.raw_h1 = carve<float>(c, R25 * 128, dry);
+        S.u1 = carve_split(c, R48 * 128, dry);
+        S.raw_h2 = carve<float>(c, R48 * 32, dry);
+        S.t = carve<float>(c, R48 * 2, dry);
+        S.bnstat = carve<float>(c, 22 * 4 * MAX_CH, dry);
+        S.valid = false; S.B = 0; S.training = 0;
+    }
+    std::vector<ConvP> convs; conv_list(d, convs);
+    for (int p = 0; p < 2; ++p) {
+        for (size_t i = 0; i < convs.size(); ++i) {
+            size_t n = (size_t)convs[i].cout * convs[i].cin * convs[i].k * convs[i].k;
+            c->packed[p].fwd[i] = carve_split(c, n, dry);
+            c->packed[p].bwd[i] = carve_split(c, n, dry);
+        }
+        c->packed[p].key = nullptr; c->packed[p].version = 0; c->packed[p].used = false;
+    }
+    c->packed_next = 0;
+    c->partials = carve<float>(c, (size_t)STAT_BLOCKS * 3 * MAX_CH, dry);
+    c->sums = carve<float>(c, 3 * MAX_CH, dry);
+    c->dpartials = carve<double>(c, 1024, dry);
+    c->G[0] = carve<float>(c, R25 * 512, dry);
+    c->G[1] = carve<float>(c, R25 * 512, dry);
+    c->g_mid = carve<float>(c, R25 * 512, dry);
+    c->du1 = carve<float>(c, R48 * 128, dry);
+    c->dt = carve<float>(c, R48 * 2, dry);
+    c->dz0 = carve<float>(c, R48 * 64, dry);
+    c->dy0 = carve<float>(c, R48 * 64, dry);
+    c->hp = carve<float>(c, (size_t)STAT_BLOCKS * 6 * 32, dry);
+    c->wscratch = carve<float>(c, umma_wgrad_scratch_floats(), dry);
+    c->stem_partials = carve<float>(c, stem_wgrad_partial_floats(d.C), dry);
+    c->dyA = carve_split(c, R25 * 512, dry);
+    c->dyB = carve_split(c, R25 * 512, dry);
+    c->dy2h = carve_split(c, R48 * 32, dry);
+    c->q_s = carve<float>(c, B * 2 * 9216, dry);
+    c->q_no = carve<float>(c, B * 2 * 9216, dry);
+    c->q_nt = carve<float>(c, B * 2 * 9216, dry);
+    c->dq = carve<float>(c, B * 2 * 9216, dry);
+    c->per_sample = carve<float>(c, B * 2, dry);
+    c->best = carve<long long>(c, B, dry);
+}
+
+extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch) {
+    if (!out) { simq_set_error("simq_ctx_create: out is NULL"); return 1; }
+    *out = nullptr;
+    if (C < 1 || C > 64 || A < 1 || A > 2 || max_batch < 1) { simq_set_error("simq_ctx_create: C=%d A=%d max_batch=%d unsupported", C, A, max_batch); return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { simq_set_error("simq_ctx_create: no CUDA device (the simq path has no CPU fallback)"); return 2; }
+    SIMQ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SIMQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { simq_set_error("simq_ctx_create: device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor); return 2; }
+    simq_ctx* c = new simq_ctx();
+    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA;
+    build_desc(c->d, C, A);
+    c->pool = nullptr;
+    carve_all(c, true);
+    c->pool_bytes = c->pool_used;
+    cudaError_t e = cudaMalloc(&c->pool, c->pool_bytes);
+    if (e != cudaSuccess) { simq_set_error("simq_ctx_create: cudaMalloc(%zu) -> %s", c->pool_bytes, cudaGetErrorString(e)); delete c; return 1; }
+    carve_all(c, false);
+    e = cudaMemset(c->pool, 0, c->pool_bytes);
+    if (e != cudaSuccess) { simq_set_error("simq_ctx_create: memset -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
+    c->launches0 = g_simq_launches;
+    if (umma_init()) { cudaFree(c->pool); delete c; return 1; }
+    *out = c;
+    return 0;
+}
+
+extern "C" void simq_ctx_destroy(simq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->pool);
+    delete c;
+}
+
+extern "C" int simq_set_backend(simq_ctx* c, int backend) {
+    if (!c || (backend != SIMQ_BACKEND_UMMA && backend != SIMQ_BACKEND_FMA)) { simq_set_error("simq_set_backend: bad argument"); return 1; }
+    c->backend = backend;
+    return 0;
+}
+extern "C" size_t simq_workspace_bytes(const simq_ctx* c) { return c ? c->pool_bytes : 0; }
+extern "C" int64_t simq_launch_count(const simq_ctx* c) { return c ? (int64_t)(g_simq_launches - c->launches0) : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static inline float* bnstat(ActSet& S, int bn, int which) { return S.bnstat + ((size_t)bn * 4 + which) * MAX_CH; }
+enum { BS_MEAN = 0, BS_INVSTD = 1, BS_SCALE = 2, BS_SHIFT = 3 };
+
+static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Split W, int N, int ntaps, float* out,
+                    ConvEpilogue ep, cudaStream_t s) {
+    if (backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
+        UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
+        return k_conv_umma(a, w, N, ntaps, out, ep, s);
+    }
+    return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, s);
+}
+static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW,
+                     cudaStream_t s) {
+    if (backend == SIMQ_BACKEND_UMMA && umma_wgrad_supported(Cout, Cin)) {
+        UmmaTensor y{dY, rows, Cout}, x{X, rows, Cin};
+        return k_wgrad_umma(y, x, ntaps, dW, c->wscratch, s);
+    }
+    return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, s);
+}
+
+static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version, cudaStream_t s, int* err) {
+    *err = 0;
+    PackedSet* ps = nullptr;
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == params) ps = &c->packed[i];
+    if (ps && version != 0 && ps->version == version) return ps;
+    if (!ps) { ps = &c->packed[c->packed_next]; c->packed_next ^= 1; }
+    std::vector<ConvP> convs; conv_list(c->d, convs);
+    for (size_t i = 0; i < convs.size(); ++i) {
+        if (k_pack_weights(params + c->d.poff[convs[i].w], convs[i].cout, convs[i].cin, convs[i].k * convs[i].k, ps->fwd[i],
+                           ps->bwd[i], s)) { *err = 1; return nullptr; }
+    }
+    ps->key = params; ps->version = version; ps->used = true;
+    return ps;
+}
+
+#define TRY(expr) do { if (expr) return 1; } while (0)
+
+// BatchNorm forward bookkeeping for one BN: fills mean/invstd/scale/shift of set S
+static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, long long rows, double count, const float* params,
+                      float* bn, int64_t* nbt, int bias_param, int training, cudaStream_t s) {
+    const NetDesc& d = c->d;
+    const float* gamma = params + d.poff[b.gamma];
+    const float* beta = params + d.poff[b.gamma + 1];
+    const float* bias = bias_param >= 0 ? params + d.poff[bias_param] : nullptr;
+    float* rmean = bn + d.bnoff[b.idx];
+    float* rvar = rmean + b.ch;
+    if (training) {
+        TRY(k_colstats(raw, rows, b.ch, c->partials, s));
+        TRY(k_bn_finalize_train(c->partials, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
+                                bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), bnstat(S, b.idx, BS_SCALE),
+                                bnstat(S, b.idx, BS_SHIFT), s));
+    } else {
+        TRY(k_bn_eval_affine(b.ch, gamma, beta, bias, rmean, rvar, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT), s));
+    }
+    return 0;
+}
+
+static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* bn, int64_t* nbt, const float* x, int B,
+                       int x_layout, int training, ActSet& S, float* q, cudaStream_t s) {
+    const NetDesc& d = c->d;
+    const long long R25 = (long long)B * IMG25, R48 = (long long)B * 2304;
+    const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
+    const int be = c->backend;
+    S.valid = false;
+    // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
+    TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
+    TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, s));
+    TRY(k_stem_pool(S.raw0, B, bnstat(S, d.stem_bn.idx, BS_SCALE), bnstat(S, d.stem_bn.idx, BS_SHIFT), S.a0, s));
+    // residual stages                                            (resnet.py:31-47, 99-102)
+    Split in = S.a0;
+    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
+    Split none{nullptr, nullptr};
+    for (int b = 0; b < 8; ++b) {
+        const BlockP& P = d.blk[b];
+        auto& A = S.blk[b];
+        const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
+        TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[s1], P.planes, 9, A.raw1, ep25, s));
+        TRY(bn_prepare(c, S, P.b1, A.raw1, R25, cnt24, params, bn, nbt, -1, training, s));
+        TRY(k_bn_apply(A.raw1, R25, P.planes, bnstat(S, P.b1.idx, BS_SCALE), bnstat(S, P.b1.idx, BS_SHIFT), 0, none, nullptr,
+                       nullptr, nullptr, 1, A.b1, s));
+        TRY(conv_any(c, be, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, A.raw2, ep25, s));
+        TRY(bn_prepare(c, S, P.b2, A.raw2, R25, cnt24, params, bn, nbt, -1, training, s));
+        if (P.has_ds) {
+            const int sd = conv_slot(d, P.ds.w);
+            TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[sd], P.planes, 1, A.rawd, ep25, s));
+            TRY(bn_prepare(c, S, P.bds, A.rawd, R25, cnt24, params, bn, nbt, -1, training, s));
+            TRY(k_bn_apply(A.raw2, R25, P.planes, bnstat(S, P.b2.idx, BS_SCALE), bnstat(S, P.b2.idx, BS_SHIFT), 2, none, A.rawd,
+                           bnstat(S, P.bds.idx, BS_SCALE), bnstat(S, P.bds.idx, BS_SHIFT), 1, A.out, s));
+        } else {
+            TRY(k_bn_apply(A.raw2, R25, P.planes, bnstat(S, P.b2.idx, BS_SCALE), bnstat(S, P.b2.idx, BS_SHIFT), 1, in, nullptr,
+                           nullptr, nullptr, 1, A.out, s));
+        }
+        in = A.out;
+    }
+    // head                                                       (networks.py:18-26)
+    TRY(conv_any(c, be, in, R25, 512, pw->fwd[conv_slot(d, d.h1.w)], 128, 1, S.raw_h1, ep25, s));
+    TRY(bn_prepare(c, S, d.hbn1, S.raw_h1, R25, cnt24, params, bn, nbt, d.h1_bias, training, s));
+    TRY(k_head_up1(S.raw_h1, B, bnstat(S, d.hbn1.idx, BS_SCALE), bnstat(S, d.hbn1.idx, BS_SHIFT), S.u1, s));
+    ConvEpilogue ep0{0, nullptr, nullptr, nullptr};
+    TRY(conv_any(c, be, S.u1, R48, 128, pw->fwd[conv_slot(d, d.h2.w)], 32, 1, S.raw_h2, ep0, s));
+    TRY(bn_prepare(c, S, d.hbn2, S.raw_h2, R48, cnt48, params, bn, nbt, d.h2_bias, training, s));
+    TRY(k_head_t(S.raw_h2, R48, bnstat(S, d.hbn2.idx, BS_SCALE), bnstat(S, d.hbn2.idx, BS_SHIFT), params + d.poff[d.h3.w], d.A,
+                 S.t, s));
+    if (q) TRY(k_head_up2(S.t, B, d.A, params + d.poff[d.h3_bias], q, s));
+    S.B = B; S.training = training; S.valid = true;
+    return 0;
+}
+
+static int check_fwd_args(simq_ctx* c, const void* params, const void* bn, const void* x, int B) {
+    if (!c) { simq_set_error("ctx is NULL"); return 1; }
+    if (!params || !bn || !x) { simq_set_error("NULL tensor pointer"); return 1; }
+    if (B < 1 || B > c->maxB) { simq_set_error("batch %d outside [1, max_batch=%d]", B, c->maxB); return 1; }
+    return 0;
+}
+
+extern "C" int simq_fcn_forward(simq_ctx* c, const float* params, float* bn, int64_t* nbt, const float* x, int B, int x_layout,
+                                int training, int save_for_backward, float* q, uint64_t params_version, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, x, B));
+    if (!q) { simq_set_error("simq_fcn_forward: q is NULL"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int err;
+    PackedSet* pw = get_packed(c, params, params_version, s, &err);
+    if (err) return 1;
+    return run_forward(c, pw, params, bn, nbt, x, B, x_layout, training, c->set[save_for_backward ? 0 : 1], q, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, long long rows, double count, int mask_mode,
+                       const bf16* mask_hi, const float* raw, const float* params, float* grads, int pitch25, Split dy,
+                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, cudaStream_t s) {
+    const NetDesc& d = c->d;
+    TRY(k_bn_bwd_reduce(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
+                        bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr,
+                        bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr, c->partials, s));
+    TRY(k_reduce_partials(c->partials, STAT_BLOCKS, 3 * b.ch, c->sums, 1.0f, s));
+    TRY(k_bn_bwd_apply(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
+                       bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), params + d.poff[b.gamma], c->sums, count, pitch25, dy,
+                       dy_f32, rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr, bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr,
+                       bd ? params + d.poff[bd->gamma] : nullptr, dyd, grads + d.poff[b.gamma], grads + d.poff[b.gamma + 1],
+                       bd ? grads + d.poff[bd->gamma] : nullptr, bd ? grads + d.poff[bd->gamma + 1] : nullptr, s));
+    return 0;
+}
+
+static int bias_grad(simq_ctx* c, Split dy, long long rows, int ch, float* out, cudaStream_t s) {
+    TRY(k_colsum_split(dy, rows, ch, c->partials, s));
+    TRY(k_reduce_partials(c->partials, STAT_BLOCKS, ch, out, 1.0f, s));
+    return 0;
+}
+
+static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const float* x, int x_layout, const float* dq, int B,
+                        float* grads, cudaStream_t s) {
+    const NetDesc& d = c->d;
+    ActSet& S = c->set[0];
+    if (!S.valid || !S.training || S.B != B) { simq_set_error("simq_fcn_backward: no matching training-mode saving forward (B=%d)", B); return 1; }
+    const long long R25 = (long long)B * IMG25, R48 = (long long)B * 2304;
+    const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
+    const int be = c->backend, A = d.A;
+    Split none{nullptr, nullptr};
+    // ---- head: upsample adjoint, conv3 + BN2 + conv2 ----
+    TRY(k_up2_adj(dq, B, A, c->dt, s));
+    const int hb2 = d.hbn2.idx;
+    TRY(k_head2_reduce(c->dt, S.raw_h2, R48, A, bnstat(S, hb2, BS_SCALE), bnstat(S, hb2, BS_SHIFT), bnstat(S, hb2, BS_MEAN),
+                       bnstat(S, hb2, BS_INVSTD), params + d.poff[d.h3.w], c->hp, s));
+    const int K2 = (2 + 2 * A) * 32;
+    TRY(k_reduce_partials(c->hp, STAT_BLOCKS, K2, c->sums, 1.0f, s));
+    TRY(k_head2_scatter(c->sums, A, grads + d.poff[d.hbn2.gamma], grads + d.poff[d.hbn2.gamma + 1], grads + d.poff[d.h3.w],
+                        grads + d.poff[d.h3_bias], s));
+    TRY(k_head2_apply(c->dt, S.raw_h2, R48, A, bnstat(S, hb2, BS_SCALE), bnstat(S, hb2, BS_SHIFT), bnstat(S, hb2, BS_MEAN),
+                      bnstat(S, hb2, BS_INVSTD), params + d.poff[d.h3.w], c->sums, cnt48, c->dy2h, s));
+    TRY(bias_grad(c, c->dy2h, R48, 32, grads + d.poff[d.h2_bias], s));
+    TRY(wgrad_any(c, be, c->dy2h, S.u1, R48, 32, 128, 1, grads + d.poff[d.h2.w], s));
+    ConvEpilogue ep0{0, nullptr, nullptr, nullptr};
+    TRY(conv_any(c, be, c->dy2h, R48, 32, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, s));
+    // ---- head: upsample adjoint, BN1 + conv1 ----
+    float* G = c->G[0];
+    float* Gn = c->G[1];
+    TRY(k_up1_adj(c->du1, B, G, s));
+    TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr, none, s));
+    TRY(bias_grad(c, c->dyA, R25, 128, grads + d.poff[d.h1_bias], s));
+    TRY(wgrad_any(c, be, c->dyA, S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w], s));
+    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
+    TRY(conv_any(c, be, c->dyA, R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, ep25, s));
+    { float* t = G; G = Gn; Gn = t; }
+    // ---- residual stages, last to first ----
+    for (int b = 7; b >= 0; --b) {
+        const BlockP& P = d.blk[b];
+        auto& Ab = S.blk[b];
+        Split in = b == 0 ? S.a0 : S.blk[b - 1].out;
+        const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
+        // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
+        TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, c->dyA, nullptr, P.has_ds ? &P.bds : nullptr,
+                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, s));
+        TRY(wgrad_any(c, be, c->dyA, Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w], s));
+        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, ep25, s));
+        if (P.has_ds) TRY(wgrad_any(c, be, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w], s));
+        // b1 = relu(bn1(raw1))
+        TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr,
+                        none, s));
+        TRY(wgrad_any(c, be, c->dyA, in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w], s));
+        ConvEpilogue ep = ep25;
+        if (!P.has_ds) { ep.add_g = G; ep.add_g_mask = Ab.out.hi; }
+        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, s));
+        if (P.has_ds) {
+            ConvEpilogue epd = ep25;
+            epd.add_prev = Gn;
+            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, s));
+        }
+        { float* t = G; G = Gn; Gn = t; }
+    }
+    // ---- stem: maxpool + ReLU + BN + conv 7x7 ----
+    const int sb = d.stem_bn.idx;
+    TRY(k_pool_bwd(G, S.raw0, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
+    TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, s));
+    TRY(k_stem_wgrad(x, x_layout, B, d.C, c->dy0, c->stem_partials, grads + d.poff[d.stem.w], s));
+    return 0;
+}
+
+extern "C" int simq_fcn_backward(simq_ctx* c, const float* params, const float* x, int x_layout, const float* dq, int B,
+                                 float* grads, simq_stream stream) {
+    if (!c || !params || !x || !dq || !grads) { simq_set_error("simq_fcn_backward: NULL argument"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    PackedSet* pw = nullptr;
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];
+    if (!pw) { simq_set_error("simq_fcn_backward: parameters were not seen by a forward"); return 1; }
+    return run_backward(c, pw, params, x, x_layout, dq, B, grads, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail, optimiser, whole step, greedy action
+// ------------------------------------------------------------------------------------------------
+extern "C" int simq_dqn_tail(simq_ctx* c, const float* q_s, const float* q_next_online, const float* q_next_target,
+                             const int64_t* action, const float* reward, const uint8_t* nonfinal, float gamma, int B, int Bn,
+                             int double_dqn, float* out2, float* dq, simq_stream stream) {
+    if (!c || !q_s || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_dqn_tail: NULL argument"); return 1; }
+    if (B < 1 || B > c->maxB || Bn < 0 || Bn > B) { simq_set_error("simq_dqn_tail: B=%d Bn=%d", B, Bn); return 1; }
+    if (Bn > 0 && (!q_next_target || (double_dqn && !q_next_online))) { simq_set_error("simq_dqn_tail: next-state Q-maps missing"); return 1; }
+    return k_dqn_tail(q_s, q_next_online, q_next_target, (const long long*)action, reward, nonfinal, gamma, B, Bn, c->d.A, double_dqn,
+                      c->per_sample, c->best, out2, dq, (cudaStream_t)stream);
+}
+
+extern "C" int simq_sgd_step(simq_ctx* c, float* params, float* grads, float* momentum, float lr, float mom, float wd,
+                             float clip_norm, int first_step, float* grad_norm_out, simq_stream stream) {
+    if (!c || !params || !grads || !momentum) { simq_set_error("simq_sgd_step: NULL argument"); return 1; }
+    return k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, grad_norm_out,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, s_, B));
+    if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
+    if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int err;
+    PackedSet* pw = get_packed(c, params, 0, s, &err);                                     // SGD changed them last step
+    if (err) return 1;
+    // train.py:114  online forward on s (train-mode BN, activations kept)
+    TRY(run_forward(c, pw, params, bn, nbt, s_, B, x_layout, 1, c->set[0], c->q_s, s));
+    if (Bn > 0) {
+        // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again)
+        if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, s));
+        // train.py:122/124  target forward, eval-mode BN
+        PackedSet* pt = get_packed(c, target_params, target_version, s, &err);
+        if (err) return 1;
+        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, s));
+        pw = nullptr;
+        for (int i = 0; i < 2; ++i)
+            if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];
+        if (!pw) { simq_set_error("simq_train_step: packed policy weights evicted"); return 1; }
+    }
+    // train.py:115-129; dL/dQ is one-hot per sample
+    float* dq = c->dq;
+    TRY(k_dqn_tail(c->q_s, c->q_no, c->q_nt, (const long long*)action, reward, nonfinal, gamma, B, Bn, c->d.A, double_dqn,
+                   c->per_sample, c->best, out2, dq, s));
+    // train.py:131-135
+    TRY(run_backward(c, pw, params, s_, x_layout, dq, B, grads, s));
+    if (apply_update)
+        TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
+    return 0;
+}
+
+extern "C" int simq_greedy_action(simq_ctx* c, const float* params, const float* bn, const float* x, int B, int x_layout,
+                                  int64_t* action_out, float* q, uint64_t params_version, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, x, B));
+    if (!action_out) { simq_set_error("simq_greedy_action: action_out is NULL"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int err;
+    PackedSet* pw = get_packed(c, params, params_version, s, &err);
+    if (err) return 1;
+    float* qq = q ? q : c->q_nt;
+    TRY(run_forward(c, pw, params, (float*)bn, nullptr, x, B, x_layout, 0, c->set[1], qq, s));
+    return k_argmax_rows(qq, B, (long long)c->d.A * 9216, (long long*)action_out, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+static const char* kDebugNames[] = {"raw0", "a0"};
+extern "C" const char* simq_debug_tensor_name(int id) {
+    static thread_local char buf[64];
+    if (id < 0) return nullptr;
+    if (id < 2) return kDebugNames[id];
+    if (id < 34) { const char* n[4] = {"raw1", "b1", "raw2", "out"}; snprintf(buf, sizeof(buf), "blk%d.%s", (id - 2) / 4, n[(id - 2) % 4]); return buf; }
+    if (id == 34) return "raw_h1";
+    if (id == 35) return "u1";
+    if (id == 36) return "raw_h2";
+    if (id == 37) return "t";
+    if (id < 46) { snprintf(buf, sizeof(buf), "blk%d.rawd", id - 38); return buf; }
+    return nullptr;
+}
+
+extern "C" int simq_debug_get(simq_ctx* c, int set, int id, int B, float* out, int64_t* chw, simq_stream stream) {
+    if (!c || set < 0 || set > 1 || !out) { simq_set_error("simq_debug_get: bad argument"); return 1; }
+    ActSet& S = c->set[set];
+    cudaStream_t s = (cudaStream_t)stream;
+    Split none{nullptr, nullptr};
+    const NetDesc& d = c->d;
+    int C = 0, HW = 24; const float* raw = nullptr; Split sp = none; bool p25 = true;
+    if (id == 0) { raw = S.raw0; C = 64; HW = 48; p25 = false; }
+    else if (id == 1) { sp = S.a0; C = 64; }
+    else if (id < 34) {
+        int b = (id - 2) / 4, w = (id - 2) % 4; C = d.blk[b].planes;
+        if (w == 0) raw = S.blk[b].raw1; else if (w == 1) sp = S.blk[b].b1; else if (w == 2) raw = S.blk[b].raw2; else sp = S.blk[b].out;
+    }
+    else if (id == 34) { raw = S.raw_h1; C = 128; }
+    else if (id == 35) { sp = S.u1; C = 128; HW = 48; p25 = false; }
+    else if (id == 36) { raw = S.raw_h2; C = 32; HW = 48; p25 = false; }
+    else if (id == 37) { raw = S.t; C = d.A; HW = 48; p25 = false; }
+    else if (id < 46) { int b = id - 38; if (!d.blk[b].has_ds) { simq_set_error("simq_debug_get: block %d has no downsample", b); return 1; } raw = S.blk[b].rawd; C = d.blk[b].planes; }
+    else { simq_set_error("simq_debug_get: unknown id %d", id); return 1; }
+    if (chw) *chw = (int64_t)C * HW * HW;
+    if (p25) return k_export_p25(raw, sp, B, C, out, s);
+    return k_export_dense(raw, sp, B, C, HW, out, s);
+}
+
+extern "C" int simq_test_conv(simq_ctx* c, int backend, int mode, int B, int Cin, int Cout, int k, const float* a, const float* a2,
+                              const float* w, float* out, simq_stream stream) {
+    if (!c || !a || !out || (mode != 2 && !w) || (mode == 2 && !a2)) { simq_set_error("simq_test_conv: NULL argument"); return 1; }
+    if (B < 1 || B > c->maxB || Cin > 512 || Cout > 512 || Cin % 16 || Cout % 16 || (k != 1 && k != 3)) { simq_set_error("simq_test_conv: bad shape"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long R25 = (long long)B * IMG25;
+    const int taps = k * k;
+    // borrow backward scratch: dyA / dyB as the operand planes, G[0] as the p25 output, packed slot 1 for the weights
+    Split X = c->dyA, Y = c->dyB;
+    Split wf = c->packed[1].fwd[15], wb = c->packed[1].bwd[15];       // layer4.1.conv2 slot: 512*512*9 elements
+    c->packed[1].used = false;
+    Split none{nullptr, nullptr};
+    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
+    if (mode == 0) {
+        TRY(k_import_p25(a, B, Cin, X, nullptr, s));
+        TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));
+        TRY(conv_any(c, backend, X, R25, Cin, wf, Cout, taps, c->G[0], ep25, s));
+        return k_export_p25(c->G[0], none, B, Cout, out, s);
+    } else if (mode == 1) {
+        TRY(k_import_p25(a, B, Cout, Y, nullptr, s));
+        TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));
+        TRY(conv_any(c, backend, Y, R25, Cout, wb, Cin, taps, c->G[0], ep25, s));
+        return k_export_p25(c->G[0], none, B, Cin, out, s);
+    } else {
+        TRY(k_import_p25(a, B, Cin, X, nullptr, s));
+        TRY(k_import_p25(a2, B, Cout, Y, nullptr, s));
+        return wgrad_any(c, backend, Y, X, R25, Cout, Cin, taps, out, s);
+    }
+}

@@ -1,0 +1,500 @@
+// tcgen05 / TMA convolutions for the 24x24 stages (sm_100a only).
+//
+// Forward conv and dgrad (k_conv_umma): the pitch-25 layout (common.cuh) turns a 3x3 conv into 9
+// row-shifted GEMMs  out[m][n] = sum_t sum_k A[m + off_t][k] * W[t][n][k]  over M = B*625 rows.
+// One CTA owns a 128 x BN output tile; a TMA producer warp streams, per (tap, 64-wide K chunk), the
+// hi and lo bf16 planes of the shifted A rows and of the W tile into a SWIZZLE_128B shared-memory
+// ring (out-of-range rows are zero-filled by TMA = the conv padding before the first / after the
+// last image); one thread issues three tcgen05.mma per K=16 step -- lo*hi, hi*lo, hi*hi -- into one
+// fp32 accumulator in TMEM (value = hi + lo carries 16 mantissa bits); four
+// epilogue warps read TMEM back with tcgen05.ld, zero the pitch-25 halo rows, optionally add a
+// residual / previous gradient and write fp32.
+//
+// wgrad (k_wgrad_umma): dW[t][co][ci] = sum_p dY[p][co] * X[p + off_t][ci] is a GEMM whose
+// contraction runs over the rows, i.e. both operands are MN-major in shared memory (rows of 64
+// channels = 128 bytes, SWIZZLE_128B).  Grid = (co tiles, ci tiles, taps x row splits); every CTA
+// writes its partial tile to a scratch buffer, a second kernel sums the splits in a fixed order
+// (deterministic) into the OIHW gradient.
+#include "kernels.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin == 1024) t0 = clock64();
+        if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread l of the warp receives row (lane base + l)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+#define UM_BM 128
+#define UM_BK 64
+#define UM_THREADS 192          // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+
+template <int BN>
+struct ConvCfg {
+    static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // one plane of the A tile (16 KB)
+    static constexpr int W_BYTES = BN * UM_BK * 2;            // one plane of the W tile
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward conv / dgrad
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                 const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, long long rows, int K,
+                 int N, int ntaps, float* __restrict__ out, ConvEpilogue ep) {
+    using Cfg = ConvCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;       // full[s], empty[s], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * UM_BM;
+    const int n0 = blockIdx.y * BN;
+    const int kchunks = K / UM_BK;
+    const int iters = ntaps * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mAhi); tma_prefetch_desc(&mAlo); tma_prefetch_desc(&mWhi); tma_prefetch_desc(&mWlo);
+    }
+    if (warp == 1) tmem_alloc<tmem_cols(BN)>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                const int t = it / kchunks, kc = it - t * kchunks;
+                const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                const int arow = (int)(m0 + off);
+                tma_load_2d(sa, &mAhi, full_bar(s), kc * UM_BK, arow);
+                tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * UM_BK, arow);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * UM_BK, t * N + n0);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * UM_BK, t * N + n0);
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < UM_BK / 16; ++k) {
+                    const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
+                    const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
+                    const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
+                    const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
+                    tc_mma_bf16(tmem_base, a_lo, w_hi, idesc, (it | k) != 0);
+                    tc_mma_bf16(tmem_base, a_hi, w_lo, idesc, 1);
+                    tc_mma_bf16(tmem_base, a_hi, w_hi, idesc, 1);
+                }
+                tc_commit(empty_bar(s));            // frees the stage once these MMAs have read it
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(accum_bar);
+        }
+    } else {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+        const long long m = m0 + quad * 32 + lane;
+        const bool in_range = m < rows;
+        const bool valid = in_range && !(ep.pitch25 && !p25_valid((int)(m % IMG25)));
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+            if (in_range) {
+                const size_t o = (size_t)m * N + n0 + c;
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                } else {
+                    if (ep.add_prev) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o + i);
+                            v[i] += p.x; v[i + 1] += p.y; v[i + 2] += p.z; v[i + 3] += p.w;
+                        }
+                    }
+                    if (ep.add_g) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float g[8];
+                            load8(ep.add_g + o + i, g);
+                            bf16x8 mk = *reinterpret_cast<const bf16x8*>(ep.add_g_mask + o + i);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (bf2f(mk.v[j]) > 0.f) v[i + j] += g[j];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<tmem_cols(BN)>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: partial[z][co][ci] = sum_{p in split} dY[p][co] * X[p + off_t][ci],  z = split*ntaps + t
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct WgradCfg {
+    static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // dY plane: 2 blocks of [64 rows][64 co]
+    static constexpr int B_BYTES = BN * UM_BK * 2;            // X plane: BN/64 blocks of [64 rows][64 ci]
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
+                  const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo, long long rows, int Cout,
+                  int Cin, int ntaps, int nsplit, long long chunk, float* __restrict__ partial) {
+    using Cfg = WgradCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.x * UM_BM, ci0 = blockIdx.y * BN;
+    const int t = blockIdx.z % ntaps, sp = blockIdx.z / ntaps;
+    const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
+    const long long p_begin = (long long)sp * chunk;
+    long long p_end = p_begin + chunk;
+    if (p_end > rows) p_end = rows;
+    const int iters = p_end > p_begin ? (int)((p_end - p_begin + UM_BK - 1) / UM_BK) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mYhi); tma_prefetch_desc(&mYlo); tma_prefetch_desc(&mXhi); tma_prefetch_desc(&mXlo);
+    }
+    if (warp == 1) tmem_alloc<tmem_cols(BN)>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                const int p0 = (int)(p_begin + (long long)it * UM_BK);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < UM_BM / 64; ++j) {
+                    tma_load_2d(sa + j * 8192, &mYhi, full_bar(s), co0 + j * 64, p0);
+                    tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &mYlo, full_bar(s), co0 + j * 64, p0);
+                }
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) {
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES + j * 8192, &mXhi, full_bar(s), ci0 + j * 64, p0 + off);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * 8192, &mXlo, full_bar(s), ci0 + j * 64, p0 + off);
+                }
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < UM_BK / 16; ++k) {
+                    // MN-major SWIZZLE_128B: 8 rows of 128 B per atom (SBO = 1024 B between 8-row groups along
+                    // K), 64-channel blocks 8 KB apart (LBO); a K=16 step is two atoms = 2048 B.
+                    const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
+                    const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
+                    const uint64_t x_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 2048, 8192, 1024);
+                    const uint64_t x_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                    tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
+                    tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
+                    tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                }
+                tc_commit(empty_bar(s));
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(accum_bar);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int co = co0 + quad * 32 + lane;
+        float* dst = partial + ((size_t)blockIdx.z * Cout + co) * Cin + ci0;
+        if (iters > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            if (iters > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (co < Cout && ci0 + c < Cin) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<tmem_cols(BN)>(tmem_base);
+    }
+}
+
+// dW[co][ci][t] (OIHW) = sum_sp partial[sp*ntaps + t][co][ci]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int Cout, int Cin, int ntaps,
+                                                           int nsplit, float* __restrict__ dW) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long per = (long long)Cout * Cin;
+    if (idx >= per * ntaps) return;
+    int t = (int)(idx / per);
+    long long r = idx - (long long)t * per;          // co*Cin + ci
+    float acc = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) acc += partial[((size_t)sp * ntaps + t) * per + r];
+    dW[(size_t)r * ntaps + t] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int umma_init() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SIMQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) { simq_set_error("cuTensorMapEncodeTiled not available"); return 1; }
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    return 0;
+}
+
+// bf16 [rows][cols] row-major, box [box_rows][64 cols], SWIZZLE_128B, zero fill out of bounds
+static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { simq_set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%d box=%d)", (int)r, rows, cols, box_rows); return 1; }
+    return 0;
+}
+
+template <int BN>
+static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    using Cfg = ConvCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    CUtensorMap mAhi, mAlo, mWhi, mWlo;
+    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
+        make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
+        return 1;
+    dim3 grid(ceil_div(A.rows, UM_BM), N / BN);
+    conv_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, A.rows, A.cols, N, ntaps, out, ep);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+bool umma_conv_supported(int K, int N) { return K % UM_BK == 0 && (N == 32 || N % 64 == 0); }
+bool umma_wgrad_supported(int Cout, int Cin) { return Cout % 64 == 0 && Cin % 64 == 0; }
+
+int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    if (umma_init()) return 1;
+    if (!umma_conv_supported(A.cols, N) || W.cols != A.cols || W.rows != (long long)ntaps * N) {
+        simq_set_error("k_conv_umma: unsupported shape K=%d N=%d", A.cols, N);
+        return 1;
+    }
+    if (N == 32) return launch_conv<32>(A, W, N, ntaps, out, ep, s);
+    if (N % 128 == 0) return launch_conv<128>(A, W, N, ntaps, out, ep, s);
+    return launch_conv<64>(A, W, N, ntaps, out, ep, s);
+}
+
+size_t umma_wgrad_scratch_floats() { return (size_t)16 << 20; }     // 64 MB
+
+template <int BN>
+static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
+    using Cfg = WgradCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        SIMQ_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    const int Cout = dY.cols, Cin = X.cols;
+    const long long rows = dY.rows;
+    CUtensorMap mYhi, mYlo, mXhi, mXlo;
+    if (make_map(&mYhi, dY.t.hi, rows, Cout, UM_BK) || make_map(&mYlo, dY.t.lo, rows, Cout, UM_BK) ||
+        make_map(&mXhi, X.t.hi, rows, Cin, UM_BK) || make_map(&mXlo, X.t.lo, rows, Cin, UM_BK))
+        return 1;
+    const int tiles = ceil_div(Cout, UM_BM) * (Cin / BN) * ntaps;
+    int nsplit = (444 + tiles - 1) / tiles;                               // ~3 waves of 148 SMs
+    long long max_split = rows / (8 * UM_BK);
+    if (max_split < 1) max_split = 1;
+    if (nsplit > max_split) nsplit = (int)max_split;
+    const size_t per_split = (size_t)ntaps * Cout * Cin;
+    while (nsplit > 1 && per_split * nsplit > umma_wgrad_scratch_floats()) --nsplit;
+    if (per_split * nsplit > umma_wgrad_scratch_floats()) { simq_set_error("wgrad scratch too small"); return 1; }
+    long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
+    dim3 grid(ceil_div(Cout, UM_BM), Cin / BN, ntaps * nsplit);
+    wgrad_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk,
+                                                                  scratch);
+    SIMQ_LAUNCH_CHECK();
+    long long n = (long long)per_split;
+    wgrad_reduce_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scratch, Cout, Cin, ntaps, nsplit, dW);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
+    if (umma_init()) return 1;
+    if (!umma_wgrad_supported(dY.cols, X.cols) || dY.rows != X.rows) {
+        simq_set_error("k_wgrad_umma: unsupported shape Cout=%d Cin=%d", dY.cols, X.cols);
+        return 1;
+    }
+    if (X.cols % 128 == 0) return launch_wgrad<128>(dY, X, ntaps, dW, scratch, s);
+    return launch_wgrad<64>(dY, X, ntaps, dW, scratch, s);
+}

@@ -1,0 +1,94 @@
+// Host-side launchers of the simq kernels.  All return 0 on success.
+#pragma once
+#include "common.cuh"
+
+#define STAT_BLOCKS 296          // 2 x 148 SMs: partial-sum slots of every column reduction
+#define MAX_CH 512
+
+// ---- forward elementwise (kernels_elem.cu) ----
+int k_colstats(const float* x, long long rows, int C, float* partials, cudaStream_t s);
+int k_bn_finalize_train(const float* partials, int C, double count, const float* gamma, const float* beta,
+                        const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
+                        float* invstd, float* scale, float* shift, cudaStream_t s);
+int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rmean,
+                     const float* rvar, float* scale, float* shift, cudaStream_t s);
+// out = relu(raw*scale+shift + residual), residual: res_mode 0 none, 1 split tensor, 2 rawd*scaled+shiftd
+int k_bn_apply(const float* raw, long long rows, int C, const float* scale, const float* shift, int res_mode,
+               Split res, const float* rawd, const float* scaled, const float* shiftd, int pitch25, Split out,
+               cudaStream_t s);
+int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift, Split a0, cudaStream_t s);
+int k_head_up1(const float* raw_h1, int B, const float* scale, const float* shift, Split u1, cudaStream_t s);
+int k_head_t(const float* raw_h2, long long rows, const float* scale, const float* shift, const float* w3, int A,
+             float* t, cudaStream_t s);
+int k_head_up2(const float* t, int B, int A, const float* b3, float* q, cudaStream_t s);
+
+// ---- DQN tail / optimiser ----
+int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const long long* action, const float* reward,
+               const unsigned char* nonfinal, float gamma, int B, int Bn, int A, int double_dqn, float* per_sample,
+               long long* best_action, float* out2, float* dq, cudaStream_t s);
+int k_argmax_rows(const float* q, int B, long long row_len, long long* idx_out, cudaStream_t s);
+int k_sgd_step(float* params, float* grads, float* momentum, long long n, float lr, float mom, float wd,
+               float clip_norm, int first_step, double* partials, float* grad_norm_out, cudaStream_t s);
+
+// ---- weight packing: OIHW fp32 -> split bf16 [tap][n][k] ----
+// fwd: n = cout, k = cin.   bwd (dgrad): n = cin, k = cout, taps flipped.
+int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split bwd, cudaStream_t s);
+
+// ---- backward elementwise ----
+int k_up2_adj(const float* dq, int B, int A, float* dt, cudaStream_t s);
+// partials layout [STAT_BLOCKS][2+2A][32] : s1, s2, dW3[a] ; db3 in partials_b [STAT_BLOCKS][A]
+int k_head2_reduce(const float* dt, const float* raw_h2, long long rows, int A, const float* scale,
+                   const float* shift, const float* mean, const float* invstd, const float* w3, float* partials,
+                   cudaStream_t s);
+int k_reduce_partials(const float* partials, int nblk, int K, float* out, float mul, cudaStream_t s);
+int k_head2_apply(const float* dt, const float* raw_h2, long long rows, int A, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, const float* w3, const float* sums, double count,
+                  Split dy, cudaStream_t s);
+int k_up1_adj(const float* du1, int B, float* g_h1, cudaStream_t s);
+// mask_mode: 0 none, 1 split hi plane > 0, 2 recompute raw*scale+shift > 0
+int k_bn_bwd_reduce(const float* G, long long rows, int C, int mask_mode, const bf16* mask_hi, const float* raw,
+                    const float* scale, const float* shift, const float* mean, const float* invstd,
+                    const float* rawd, const float* meand, const float* invstdd, float* partials, cudaStream_t s);
+// sums: [3][C] = s1, s2, s2d (already reduced).  Writes dgamma/dbeta (and the ds pair) into grads.
+int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const bf16* mask_hi, const float* raw,
+                   const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
+                   const float* sums, double count, int pitch25, Split dy, float* dy_f32, const float* rawd,
+                   const float* meand, const float* invstdd, const float* gammad, Split dyd, float* dgamma,
+                   float* dbeta, float* dgammad, float* dbetad, cudaStream_t s);
+int k_pool_bwd(const float* g_a0, const float* raw0, int B, const float* scale, const float* shift, float* dz0,
+               cudaStream_t s);
+int k_colsum_split(Split dy, long long rows, int C, float* partials, cudaStream_t s);   // bias grads: [STAT_BLOCKS][C]
+// head2 parameter gradients out of the reduced sums [2+2A][32]: dbeta2, dgamma2, dW3, db3
+int k_head2_scatter(const float* sums, int A, float* dgamma2, float* dbeta2, float* dW3, float* db3, cudaStream_t s);
+
+// ---- debug export: internal layouts -> dense NCHW f32 ----
+int k_export_p25(const float* raw, Split sp, int B, int C, float* out, cudaStream_t s);          // 24x24
+int k_export_dense(const float* raw, Split sp, int B, int C, int HW, float* out, cudaStream_t s); // HWxHW NHWC
+int k_import_p25(const float* nchw, int B, int C, Split sp, float* raw, cudaStream_t s);
+
+// ---- FMA convolutions (conv_fma.cu): fp32 comparator + the stem ----
+struct ConvEpilogue {
+    int pitch25;              // zero the halo rows of the pitch-25 layout
+    const float* add_prev;    // out += add_prev (may alias out)
+    const float* add_g;       // out += (mask_hi > 0 ? add_g : 0)  (residual gradient)
+    const bf16* add_g_mask;
+};
+// out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
+int k_conv_fma(Split A, long long rows, int K, Split W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
+// dW[co][ci][tap] (OIHW) = sum_p dY[p][co] * X[p+off_tap][ci]   (zero-inits dW itself)
+int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW, cudaStream_t s);
+int k_stem_conv(const float* x, int x_layout, int B, int C, const float* w, float* raw0, cudaStream_t s);
+int k_stem_wgrad(const float* x, int x_layout, int B, int C, const float* dy0, float* partials, float* dW,
+                 cudaStream_t s);
+size_t stem_wgrad_partial_floats(int C);
+
+// ---- tcgen05 convolutions (conv_umma.cu) ----
+struct UmmaTensor {          // a split tensor plus its row count / width, enough to build tensor maps
+    Split t; long long rows; int cols;
+};
+int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
+int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s);
+int umma_init();             // resolves cuTensorMapEncodeTiled
+bool umma_conv_supported(int K, int N);
+bool umma_wgrad_supported(int Cout, int Cin);
+size_t umma_wgrad_scratch_floats();

@@ -1,0 +1,276 @@
+"""Drop-in for the reference's ``networks.FCN`` (networks.py:6-26 over resnet.py:50-120), computed by
+the simq CUDA library (``include/simq.h``) instead of ``torch.nn`` layers.
+
+Same constructor, same parameter / buffer names and shapes (so ``state_dict()`` /
+``load_state_dict()`` round-trip reference checkpoints, incl. the never-executed
+``resnet18.fc.*``), same ``forward(x: (N,C,96,96) f32) -> (N,A,96,96) f32`` with BatchNorm behaviour
+following ``.training``, differentiable through a ``torch.autograd.Function`` so a stock
+``torch.optim.SGD`` over ``net.parameters()`` works.
+
+All 70 trainable tensors are views into ONE flat fp32 device buffer (``flat_params``), BN running
+statistics into ``flat_bn`` and the 22 ``num_batches_tracked`` counters into ``flat_nbt`` -- the
+layout ``simq_layout`` reports -- so the fused step (``train.train``) hands the library three
+pointers.  There is no PyTorch fallback: without the CUDA library / a B200 ``forward`` raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+STAGE_PLANES = (64, 128, 256, 512)
+DEFAULT_MAX_BATCH = 32
+
+
+class _P(nn.Module):
+    """A named bag of parameters / buffers (stands in for Conv2d / BatchNorm2d / Linear)."""
+
+
+def _conv(shape, bias=False):
+    m = _P()
+    m.weight = nn.Parameter(torch.empty(shape))
+    if bias:
+        m.bias = nn.Parameter(torch.empty(shape[0]))
+    return m
+
+
+def _bn(ch):
+    m = _P()
+    m.weight = nn.Parameter(torch.ones(ch))
+    m.bias = nn.Parameter(torch.zeros(ch))
+    m.register_buffer('running_mean', torch.zeros(ch))
+    m.register_buffer('running_var', torch.ones(ch))
+    m.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+    return m
+
+
+def _block(inpl, planes, downsample):          # resnet.py:19-29
+    m = _P()
+    m.conv1 = _conv((planes, inpl, 3, 3)); m.bn1 = _bn(planes)
+    m.conv2 = _conv((planes, planes, 3, 3)); m.bn2 = _bn(planes)
+    if downsample:                              # resnet.py:79-83
+        m.downsample = nn.Sequential(_conv((planes, inpl, 1, 1)), _bn(planes))
+    return m
+
+
+def _resnet18(num_input_channels):             # resnet.py:52-68
+    m = _P()
+    m.conv1 = _conv((64, num_input_channels, 7, 7)); m.bn1 = _bn(64)
+    inpl = 64
+    for li, planes in enumerate(STAGE_PLANES, start=1):
+        setattr(m, f'layer{li}', nn.Sequential(_block(inpl, planes, inpl != planes), _block(planes, planes, False)))
+        inpl = planes
+    m.fc = _P()
+    m.fc.weight = nn.Parameter(torch.empty(1000, 512))
+    m.fc.bias = nn.Parameter(torch.empty(1000))
+    return m
+
+
+class _FCNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        q, token = net._run_forward(x, training=net.training, save=True)
+        ctx.net, ctx.token, ctx.x = net, token, x
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        views = ctx.net._run_backward(ctx.x, dq.contiguous(), ctx.token)
+        return (None, None) + tuple(views)
+
+
+class FCN(nn.Module):
+    def __init__(self, num_input_channels=3, num_output_channels=1, max_batch: int = DEFAULT_MAX_BATCH):
+        super().__init__()
+        self.num_input_channels, self.num_output_channels = num_input_channels, num_output_channels
+        self.resnet18 = _resnet18(num_input_channels)
+        self.conv1 = _conv((128, 512, 1, 1), bias=True); self.bn1 = _bn(128)
+        self.conv2 = _conv((32, 128, 1, 1), bias=True); self.bn2 = _bn(32)
+        self.conv3 = _conv((num_output_channels, 32, 1, 1), bias=True)
+        self._init_like_reference()
+        self.max_batch = max_batch
+        self._ctx = None
+        self._token = 0
+        self._manual_version = 0
+        self._flat_grad = None
+        self.flat_momentum = None
+        self.momentum_initialized = False
+        self._layout = None
+        self._flatten()
+
+    # ---- initialisation: resnet.py:70-75 + torch defaults for the head convs / fc ----
+    def _init_like_reference(self):
+        for name, p in self.named_parameters():
+            if p.dim() == 4 and name.startswith('resnet18.'):
+                nn.init.kaiming_normal_(p, mode='fan_out', nonlinearity='relu')
+            elif p.dim() >= 2:                  # head convs, fc: Conv2d / Linear default
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+        for conv in (self.conv1, self.conv2, self.conv3, self.resnet18.fc):
+            fan_in = conv.weight[0].numel()
+            nn.init.uniform_(conv.bias, -1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in))
+
+    # ---- flat storage ----
+    def trainable(self) -> List[Tuple[str, nn.Parameter]]:
+        return [(n, p) for n, p in self.named_parameters() if not n.startswith('resnet18.fc.')]
+
+    def _flatten(self):
+        """(Re)build the flat buffers on the parameters' current device and re-point every
+        parameter / buffer at its slice.  Called at construction and after ``.to()/.cuda()``."""
+        tr = self.trainable()
+        dev = tr[0][1].device
+        if self._layout is None:
+            n_p, n_b, po, bo = (sum(p.numel() for _, p in tr), None, None, None)
+            try:
+                n_p, n_b, po, bo = _lib.layout(self.num_input_channels, self.num_output_channels)
+            except _lib.SimqError:
+                po = [0]
+                for _, p in tr:
+                    po.append(po[-1] + p.numel())
+                bo = [0]
+                for _, m in self._bns():
+                    bo.append(bo[-1] + 2 * m.weight.numel())
+                n_b = bo[-1]
+            assert len(po) == len(tr) + 1 and all(po[i + 1] - po[i] == p.numel() for i, (_, p) in enumerate(tr)), \
+                'simq_layout disagrees with the module definition'
+            self._layout = (n_p, n_b, po, bo)
+        n_p, n_b, po, bo = self._layout
+        flat = torch.empty(n_p, dtype=torch.float32, device=dev)
+        for i, (_, p) in enumerate(tr):
+            flat[po[i]:po[i + 1]].copy_(p.data.reshape(-1))
+            p.data = flat[po[i]:po[i + 1]].view(p.shape)
+        bns = self._bns()
+        fbn = torch.empty(n_b, dtype=torch.float32, device=dev)
+        nbt = torch.empty(len(bns), dtype=torch.int64, device=dev)
+        for i, (_, m) in enumerate(bns):
+            ch = m.weight.numel()
+            fbn[bo[i]:bo[i] + ch].copy_(m.running_mean)
+            fbn[bo[i] + ch:bo[i] + 2 * ch].copy_(m.running_var)
+            nbt[i] = m.num_batches_tracked
+            m._buffers['running_mean'] = fbn[bo[i]:bo[i] + ch]
+            m._buffers['running_var'] = fbn[bo[i] + ch:bo[i] + 2 * ch]
+            m._buffers['num_batches_tracked'] = nbt[i]
+        self.flat_params, self.flat_bn, self.flat_nbt = flat, fbn, nbt
+        self._tr_cache = [p for _, p in tr]
+        self._manual_version += 1
+        self._flat_grad = None
+        if self.flat_momentum is not None:
+            self.flat_momentum = self.flat_momentum.to(dev)
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+    def _bns(self):
+        return [(n, m) for n, m in self.named_modules() if isinstance(m, _P) and 'running_mean' in m._buffers]
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        self._flatten()
+        return self
+
+    @property
+    def params_version(self) -> int:
+        """Changes whenever any parameter may have changed (in-place torch updates bump the tensors'
+        version counters; the fused step bumps ``_manual_version``) -> the library re-packs weights."""
+        return 1 + self._manual_version + int(self.flat_params._version) + sum(int(p._version) for p in self._tr_cache)
+
+    # ---- device context ----
+    def ctx(self, batch: int = 1) -> _lib.Ctx:
+        dev = self.flat_params.device
+        if dev.type != 'cuda':
+            raise _lib.SimqError('spatial_intention_maps_b200.networks.FCN runs only on a CUDA (B200) device; '
+                                 f'parameters are on {dev}. There is no CPU fallback.')
+        if self._ctx is None or self._ctx.max_batch < batch:
+            if self._ctx is not None:
+                torch.cuda.synchronize(dev)
+                self._ctx.close()
+            self.max_batch = max(self.max_batch, batch)
+            self._ctx = _lib.Ctx(dev.index if dev.index is not None else torch.cuda.current_device(),
+                                 self.num_input_channels, self.num_output_channels, self.max_batch)
+        return self._ctx
+
+    def set_backend(self, backend: int):
+        _lib.check(_lib.lib().simq_set_backend(self.ctx().handle, backend), 'simq_set_backend')
+
+    @staticmethod
+    def _x_layout(x):
+        if x.dim() != 4 or x.dtype != torch.float32:
+            raise ValueError(f'expected a float32 (N,C,96,96) tensor, got {tuple(x.shape)} {x.dtype}')
+        if x.is_contiguous():
+            return x, _lib.X_NCHW
+        if x.is_contiguous(memory_format=torch.channels_last):
+            return x, _lib.X_NHWC          # same bytes as an (N,96,96,C) array: no transpose pass
+        return x.contiguous(), _lib.X_NCHW
+
+    def _run_forward(self, x, training: bool, save: bool):
+        if x.shape[1] != self.num_input_channels or x.shape[2] != 96 or x.shape[3] != 96:
+            raise ValueError(f'expected (N,{self.num_input_channels},96,96), got {tuple(x.shape)}')
+        B = x.shape[0]
+        c = self.ctx(B)
+        x, lay = self._x_layout(x)
+        q = torch.empty((B, self.num_output_channels, 96, 96), dtype=torch.float32, device=x.device)
+        if save:
+            self._token += 1
+        _lib.check(_lib.lib().simq_fcn_forward(
+            c.handle, _lib.ptr(self.flat_params), _lib.ptr(self.flat_bn), _lib.ptr(self.flat_nbt), _lib.ptr(x), B, lay,
+            1 if training else 0, 1 if save else 0, _lib.ptr(q), self.params_version, _lib.stream_ptr()), 'simq_fcn_forward')
+        self._saved_x = x if save else getattr(self, '_saved_x', None)
+        return q, self._token
+
+    def _run_backward(self, x, dq, token):
+        if token != self._token:
+            raise _lib.SimqError('only the most recent grad-enabled forward of this FCN can be differentiated '
+                                 '(one saved activation set per network)')
+        x, lay = self._x_layout(x)
+        tr = self.trainable()
+        alias = self._flat_grad is not None and any(
+            p.grad is not None and p.grad.untyped_storage().data_ptr() == self._flat_grad.untyped_storage().data_ptr()
+            for _, p in tr[:1])
+        if self._flat_grad is None or alias:
+            self._flat_grad = torch.empty_like(self.flat_params)
+        g = self._flat_grad
+        _lib.check(_lib.lib().simq_fcn_backward(self.ctx().handle, _lib.ptr(self.flat_params), _lib.ptr(x), lay, _lib.ptr(dq),
+                                                x.shape[0], _lib.ptr(g), _lib.stream_ptr()), 'simq_fcn_backward')
+        po = self._layout[2]
+        return [g[po[i]:po[i + 1]].view(p.shape) for i, (_, p) in enumerate(tr)]
+
+    def flat_grad(self) -> torch.Tensor:
+        if self._flat_grad is None:
+            self._flat_grad = torch.zeros_like(self.flat_params)
+        return self._flat_grad
+
+    def forward(self, x):
+        tr = [p for _, p in self.trainable()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in tr):
+            if not self.training:
+                raise _lib.SimqError('differentiating an eval-mode forward is not supported (the reference never does)')
+            return _FCNFunction.apply(self, x, *tr)
+        return self._run_forward(x, self.training, save=False)[0]
+
+    def greedy_action(self, x, want_q: bool = False):
+        """Eval-mode forward + per-sample flat first-max argmax on the device (policies.py:56-64)."""
+        B = x.shape[0]
+        c = self.ctx(B)
+        x, lay = self._x_layout(x)
+        act = torch.empty(B, dtype=torch.int64, device=x.device)
+        q = torch.empty((B, self.num_output_channels, 96, 96), dtype=torch.float32, device=x.device) if want_q else None
+        _lib.check(_lib.lib().simq_greedy_action(c.handle, _lib.ptr(self.flat_params), _lib.ptr(self.flat_bn), _lib.ptr(x), B, lay,
+                                                 _lib.ptr(act), _lib.ptr(q), self.params_version, _lib.stream_ptr()),
+                   'simq_greedy_action')
+        return act, q
+
+
+class SingleDeviceParallel(nn.Module):
+    """Stands in for the ``torch.nn.DataParallel`` wrapper of policies.py:39-41: keeps the ``module.``
+    state_dict prefix of reference checkpoints, but never replicates -- this framework is one
+    process per GPU (gradient all-reduce over NCCL, see train.py)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)

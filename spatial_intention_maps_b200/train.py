@@ -1,0 +1,169 @@
+"""Drop-in for the reference's ``train.train`` (train.py:108-141): one Double-DQN update of a
+``networks.FCN`` -- same signature, same returned ``{'td_error', 'loss'}`` Python floats -- executed as
+ONE call into the simq CUDA library (``simq_train_step``: online forward on s, train-mode online
+forward on s', eval-mode target forward, gather / arg-max / TD target / SmoothL1, backward, global
+grad-norm clip, momentum-SGD), instead of ~450 eager kernels.
+
+The caller keeps passing its stock ``torch.optim.SGD``: learning rate, momentum and weight decay are
+read from ``optimizer.param_groups[0]`` and the momentum buffers live in the optimizer's state as
+views of the network's flat momentum vector, so ``optimizer.state_dict()`` checkpoints (train.py:324)
+stay valid.
+
+Data parallel: when ``torch.distributed`` is initialised with world_size > 1 every rank runs the step
+on its shard of the minibatch up to the gradients, the flat fp32 gradient vector is all-reduced once
+(NCCL over NVLink; mean), and every rank applies the identical clip + SGD.  BatchNorm statistics stay
+per rank, as under the reference's ``DataParallel`` (policies.py:39).
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .networks import FCN
+
+Transition = namedtuple('Transition', ('state', 'action', 'reward', 'next_state'))     # train.py:26
+
+
+def _unwrap(net) -> FCN:
+    m = getattr(net, 'module', net)
+    if not isinstance(m, FCN):
+        raise TypeError('spatial_intention_maps_b200.train.train needs spatial_intention_maps_b200.networks.FCN nets')
+    return m
+
+
+class HostBatch:
+    """Pinned host staging for one replay minibatch in NHWC (the layout ``Mapper.get_state`` already
+    produces, envs.py:2067-2184), replacing the per-sample ``transform_fn`` + ``torch.cat`` of
+    train.py:109-112.  Reused across steps to avoid re-pinning."""
+
+    def __init__(self, B: int, C: int):
+        self.B, self.C = B, C
+        pin = torch.cuda.is_available()
+        self.s = torch.empty((B, 96, 96, C), dtype=torch.float32, pin_memory=pin)
+        self.ns = torch.empty((B, 96, 96, C), dtype=torch.float32, pin_memory=pin)
+        self.action = torch.empty(B, dtype=torch.int64, pin_memory=pin)
+        self.reward = torch.empty(B, dtype=torch.float32, pin_memory=pin)
+        self.nonfinal = torch.empty(B, dtype=torch.uint8, pin_memory=pin)
+        self.Bn = 0
+
+    def fill(self, batch):
+        B = self.B
+        if len(batch.state) != B:
+            raise ValueError(f'batch has {len(batch.state)} transitions, expected {B}')
+        s_np, ns_np = self.s.numpy(), self.ns.numpy()
+        j = 0
+        for i in range(B):
+            s_np[i] = batch.state[i]
+            nxt = batch.next_state[i]
+            self.nonfinal[i] = 0 if nxt is None else 1
+            if nxt is not None:                      # train.py:112: non-terminal rows only, in order
+                ns_np[j] = nxt
+                j += 1
+        self.Bn = j
+        self.action.numpy()[:] = np.asarray(batch.action, dtype=np.int64)
+        self.reward.numpy()[:] = np.asarray(batch.reward, dtype=np.float32)
+        return self
+
+    def h2d_bytes(self) -> int:
+        return (self.B + self.Bn) * 96 * 96 * self.C * 4 + self.B * (8 + 4 + 1)
+
+
+class DeviceBatch:
+    def __init__(self, B: int, C: int, device):
+        self.s = torch.empty((B, 96, 96, C), dtype=torch.float32, device=device)
+        self.ns = torch.empty((B, 96, 96, C), dtype=torch.float32, device=device)
+        self.action = torch.empty(B, dtype=torch.int64, device=device)
+        self.reward = torch.empty(B, dtype=torch.float32, device=device)
+        self.nonfinal = torch.empty(B, dtype=torch.uint8, device=device)
+        self.out2 = torch.zeros(2, dtype=torch.float32, device=device)
+        self.out2_host = torch.zeros(2, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        self.Bn = 0
+
+    def upload(self, hb: HostBatch):
+        self.s.copy_(hb.s, non_blocking=True)
+        if hb.Bn:
+            self.ns[:hb.Bn].copy_(hb.ns[:hb.Bn], non_blocking=True)
+        self.action.copy_(hb.action, non_blocking=True)
+        self.reward.copy_(hb.reward, non_blocking=True)
+        self.nonfinal.copy_(hb.nonfinal, non_blocking=True)
+        self.Bn = hb.Bn
+        return self
+
+
+def _momentum_views(net: FCN, optimizer):
+    """Make the optimizer's momentum buffers views of the net's flat momentum vector (once)."""
+    if net.flat_momentum is None or net.flat_momentum.device != net.flat_params.device:
+        net.flat_momentum = torch.zeros_like(net.flat_params)
+        net.momentum_initialized = False
+    if getattr(net, '_momentum_bound_to', None) is optimizer:
+        return
+    po = net._layout[2]
+    have = 0
+    for i, (_, p) in enumerate(net.trainable()):
+        view = net.flat_momentum[po[i]:po[i + 1]].view(p.shape)
+        st = optimizer.state[p]
+        buf = st.get('momentum_buffer')
+        if buf is not None and buf.data_ptr() != view.data_ptr():     # resumed checkpoint (train.py:200-210)
+            view.copy_(buf)
+            have += 1
+        st['momentum_buffer'] = view
+    if have:
+        net.momentum_initialized = True
+    net._momentum_bound_to = optimizer
+
+
+def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: int, discount_factor: float,
+                      grad_norm_clipping, use_double_dqn: bool = True):
+    """The device part of one update on an uploaded batch; leaves (loss, td_error) in ``db.out2``."""
+    g = optimizer.param_groups[0]
+    if g.get('nesterov') or g.get('dampening', 0) != 0:
+        raise _lib.SimqError('the fused step implements SGD(momentum, weight_decay) without nesterov/dampening (train.py:186)')
+    _momentum_views(policy, optimizer)
+    ctx = policy.ctx(B)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    clip = float(grad_norm_clipping) if grad_norm_clipping is not None else 0.0
+    first = 0 if policy.momentum_initialized else 1
+    lr, mom, wd = float(g['lr']), float(g.get('momentum', 0.0)), float(g.get('weight_decay', 0.0))
+    grads = policy.flat_grad()
+    L = _lib.lib()
+    _lib.check(L.simq_train_step(
+        ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(policy.flat_bn), _lib.ptr(policy.flat_nbt),
+        _lib.ptr(target.flat_params), _lib.ptr(target.flat_bn), target.params_version, _lib.ptr(grads),
+        _lib.ptr(policy.flat_momentum), _lib.ptr(db.s), _lib.ptr(db.ns), _lib.X_NHWC, _lib.ptr(db.action),
+        _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, float(discount_factor), lr, mom, wd, clip, first,
+        1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(db.out2), _lib.stream_ptr()), 'simq_train_step')
+    if world > 1:
+        dist.all_reduce(grads)                      # the path's one exchange: flat fp32 gradients, sum
+        grads.mul_(1.0 / world)
+        dist.all_reduce(db.out2)                    # 2 floats: report the global-batch loss / td_error
+        db.out2.mul_(1.0 / world)
+        _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(grads), _lib.ptr(policy.flat_momentum),
+                                   lr, mom, wd, clip, first, None, _lib.stream_ptr()), 'simq_sgd_step')
+    policy.momentum_initialized = True
+    policy._manual_version += 1
+
+
+def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_factor):
+    """train.py:108-141 with the same arguments.  ``transform_fn`` is accepted for signature
+    compatibility; states are staged NHWC (``ToTensor`` on float32 input is only a transpose,
+    policies.py:44-45, which the stem kernel absorbs)."""
+    policy, target = _unwrap(policy_net), _unwrap(target_net)
+    B = int(cfg.batch_size)
+    C = policy.num_input_channels
+    dev = policy.flat_params.device
+    cache = policy.__dict__.setdefault('_batch_cache', {})
+    if cache.get('key') != (B, C, dev):
+        cache.clear()
+        cache.update(key=(B, C, dev), host=HostBatch(B, C), dev=DeviceBatch(B, C, dev))
+    hb, db = cache['host'], cache['dev']
+    hb.fill(batch)
+    db.upload(hb)
+    train_step_device(policy, target, optimizer, db, B, discount_factor, getattr(cfg, 'grad_norm_clipping', None),
+                      bool(getattr(cfg, 'use_double_dqn', True)))
+    db.out2_host.copy_(db.out2, non_blocking=True)
+    torch.cuda.current_stream().synchronize()       # the reference syncs here too: two .item() calls (train.py:138-139)
+    return {'td_error': float(db.out2_host[1]), 'loss': float(db.out2_host[0])}

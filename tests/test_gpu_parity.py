@@ -1,0 +1,153 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle and the committed golden
+fixtures.  Runs on the B200 box: ``pytest -m gpu``.
+
+Tolerances (BASELINE.json north_star): Q-map max|d|/max|Q| <= 1e-3 in fp32, per-sample arg-max action
+index equal (a differing index is accepted only if the oracle's own Q-values at the two indices
+differ by <= 1e-6 max|Q|: fp32 reduction order cannot be matched bit-for-bit)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+QTOL = 1e-3
+G = None
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_gpu():
+    global G
+    assert torch.cuda.is_available(), 'gpu-marked tests need a CUDA device'
+    from tests import gpu_checks
+    G = gpu_checks
+
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.mark.parametrize('backend', [0, 1], ids=['umma', 'fma'])
+@pytest.mark.parametrize('mode', [0, 1, 2], ids=['fwd', 'dgrad', 'wgrad'])
+def test_conv_kernels_match_torch_fp64(backend, mode):
+    from spatial_intention_maps_b200 import _lib
+    ctx = _lib.Ctx(0, 4, 2, 3)
+    for (ci, co, k) in G.CONV_SHAPES:
+        e = G.conv_check(ci, co, k, mode, backend, B=3, ctx=ctx)
+        assert e < 2e-4, f'{ci}->{co} k{k} mode {mode} backend {backend}: rel err {e:.3e}'
+    ctx.close()
+
+
+@pytest.mark.parametrize('C,A', [(4, 2), (5, 2), (5, 1), (8, 2), (3, 2), (10, 2)])
+def test_forward_matches_golden(C, A):
+    """Fixtures were produced by the reference's own networks.FCN (tests/golden/make_golden.py)."""
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import synth
+    g = np.load(os.path.join(GOLD, 'forward.npz'))
+    key = f'C{C}_A{A}'
+    seed = int(g[key + '_seed'])
+    net, st = G.make_net(C, A, seed, max_batch=2)
+    x = O.hwc_to_nchw(list(synth.synth_states(2, C, seed))).to(G.DEV)
+    with torch.no_grad():
+        net.eval()
+        q_eval = net(x).cpu()
+        net.train()
+        q_train = net(x).cpu()
+    for mine, ref in ((q_eval, torch.from_numpy(g[key + '_q_eval'])), (q_train, torch.from_numpy(g[key + '_q_train']))):
+        assert G.relerr(mine, ref) <= QTOL
+        eq, near, B = G.argmax_agreement(mine, ref)
+        assert eq + near == B
+    sd = net.state_dict()
+    np.testing.assert_allclose(sd['bn1.running_mean'].cpu().numpy(), g[key + '_bn1_rm'], rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(sd['bn1.running_var'].cpu().numpy(), g[key + '_bn1_rv'], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(sd['resnet18.layer4.1.bn2.running_mean'].cpu().numpy(), g[key + '_l4_rm'], rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(sd['resnet18.layer4.1.bn2.running_var'].cpu().numpy(), g[key + '_l4_rv'], rtol=2e-3, atol=1e-6)
+    assert int(sd['bn2.num_batches_tracked']) == int(g[key + '_nbt'])
+
+
+@pytest.mark.parametrize('training', [False, True])
+def test_forward_every_layer_matches_oracle(training):
+    errs, q, qr, bn = G.forward_trace_check(5, 2, 4, 105, training)
+    bad = {k: v for k, v in errs.items() if v > QTOL}
+    assert not bad, f'layers above tolerance: {bad}'
+    eq, near, B = G.argmax_agreement(q, qr)
+    assert eq + near == B
+    assert bn < 2e-3
+
+
+def test_nchw_and_nhwc_inputs_agree():
+    net, _ = G.make_net(5, 2, 7, max_batch=3)
+    net.eval()
+    from spatial_intention_maps_b200 import synth
+    x = torch.from_numpy(synth.synth_states(3, 5, 7)).to(G.DEV)            # (3,96,96,5) NHWC
+    with torch.no_grad():
+        a = net(x.permute(0, 3, 1, 2))                                      # channels_last view
+        b = net(x.permute(0, 3, 1, 2).contiguous())                         # NCHW copy
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('key', ['c1', 'c2', 'traj'])
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'autograd'])
+def test_dqn_step_matches_oracle_and_golden(key, fused):
+    """c1 / c2 of BASELINE.json and a 3-step trajectory; the golden losses come from the reference's own
+    train.train (tests/golden/steps.npz)."""
+    g = np.load(os.path.join(GOLD, 'steps.npz'))
+    C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
+    r = G.train_step_check(C, A, B, seed, float(g[key + '_gamma']), te, nsteps, fused=fused)
+    np.testing.assert_allclose(r['loss'][0], g[key + '_loss'][0], rtol=2e-3)
+    np.testing.assert_allclose(r['td'][0], g[key + '_td'][0], rtol=2e-3)
+    np.testing.assert_allclose(r['loss'], r['loss_ref'], rtol=5e-3 if nsteps > 1 else 2e-3)
+    worst = max(r['grad_rel_l2'].items(), key=lambda kv: kv[1])
+    assert worst[1] < 5e-3, f'gradient {worst[0]} rel-L2 {worst[1]:.3e}'
+    assert abs(r['grad_norm'] - r['grad_norm_ref']) <= 2e-3 * r['grad_norm_ref']
+    worst = max(r['param_rel_l2'].items(), key=lambda kv: kv[1])
+    assert worst[1] < (1e-4 if nsteps == 1 else 1e-3), f'parameter {worst[0]} rel-L2 {worst[1]:.3e}'
+    assert r['bn_err'] < 5e-3
+    assert r['nbt'] == r['nbt_ref'] == list(g[key + '_nbt'])
+    assert r['fc_untouched']
+    if r['mom_rel_l2'] is not None:
+        assert max(r['mom_rel_l2'].values()) < (5e-3 if nsteps == 1 else 5e-2)
+
+
+def test_policy_step_matches_golden():
+    """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import policies, synth
+    g = np.load(os.path.join(GOLD, 'policy_step.npz'))
+    C, A, seed = [int(v) for v in g['cfg']]
+    pol = policies.DQNPolicy(G.Cfg(16, C), train=False)
+    pol.policy_nets[0].module.load_state_dict(O.make_state(C, A, seed))
+    states = synth.synth_states(16, C, seed)
+    for i in range(16):
+        a, info = pol.step([[states[i]]], exploration_eps=0.0, debug=True)
+        q = info['output'][0][0]
+        assert abs(float(q.max()) - float(g['qmax'][i])) <= QTOL * max(1.0, abs(float(g['qmax'][i])))
+        if a[0][0] != int(g['actions'][i]):          # near-tie policy
+            ref_q = O.greedy_action(O.make_state(C, A, seed), states[i])[1].reshape(-1)
+            assert ref_q[int(g['actions'][i])] - ref_q[a[0][0]] <= 1e-6 * np.abs(ref_q).max()
+
+
+def test_full_size_properties_b128():
+    """c3 size (B=128, C=5, A=1): eval forward is per-sample independent (a sample's Q-map does not
+    depend on its batch-mates), greedy_action == arg-max of the forward, and a train step is finite,
+    moves the parameters and bumps num_batches_tracked by 2."""
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    net, st = G.make_net(5, 1, 13, max_batch=128)
+    x = torch.from_numpy(synth.synth_states(128, 5, 13)).to(G.DEV).permute(0, 3, 1, 2)
+    net.eval()
+    with torch.no_grad():
+        q = net(x)
+        q_sub = net(x[5:9])
+        act, _ = net.greedy_action(x)
+    assert G.relerr(q_sub, q[5:9]) < 1e-6
+    assert torch.equal(act, q.view(128, -1).argmax(1))
+    tgt = networks.FCN(5, 1, max_batch=128)
+    tgt.load_state_dict(st)
+    tgt = tgt.to(G.DEV).eval()
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    before = net.flat_params.clone()
+    info = T.train(G.Cfg(128, 5), net, tgt, opt, synth.synth_batch(128, 5, 1, 13), None, 0.85)
+    assert np.isfinite(info['loss']) and np.isfinite(info['td_error'])
+    assert torch.isfinite(net.flat_params).all() and not torch.equal(before, net.flat_params)
+    assert int(net.bn1.num_batches_tracked) == 3 + 2
