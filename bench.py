@@ -1,0 +1,286 @@
+"""Benchmark of the DQN Q-map training step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl simq|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full ``train.train`` update (train.py:108-141) on one synthetic replay minibatch:
+online forward on s, train-mode online forward on s' (Double-DQN arg-max), eval-mode target forward,
+TD target + SmoothL1, backward, global grad-norm clip, momentum-SGD.  Workload at every N: config c3 of
+SURVEY.md §8 (BASELINE.json configs[2]: pushing_4-large_empty, C=5 input channels incl. the intention
+map, A=1, gamma 0.85, batch 128 PER GPU -> weak scaling), every 64th transition terminal.
+
+``value``  : samples/s with the batch already resident in HBM (device part of the step only).
+``e2e``    : samples/s through the public API call a user makes (``train.train`` semantics): pinned host
+             batch -> H2D copies -> step -> D2H read of (loss, td_error), all inside the timed region.
+``roofline``: the dominant kernel (tcgen05 conv/dgrad), algorithmic FLOPs / CUDA-event time measured on
+             the launching stream during the timed steps, against MEASURED_PEAKS.json's sustained bf16 peak.
+``--impl reference``: the reference path on the host cores (oracle port of train.train: the reference is
+             Python and /root/reference does not exist on the GPU box), bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'DQN Q-map train-step samples/sec (3 fwd + bwd + clip + SGD, batch 128/GPU, 96x96)'
+UNIT = 'samples/s'
+C_IN, A_OUT, GAMMA, TERMINAL_EVERY = 5, 1, 0.85, 64
+FWD_GFLOP = 13.021 - 0.0006            # per sample, C=5, A=1
+STEP_GFLOP = 5 * FWD_GFLOP - 0.0723    # 3 forwards + backward (2x forward, no stem dgrad)
+CPU_SAMPLE_B = 16
+
+
+def workload_name(B):
+    return f'c3 pushing_4-large_empty: C={C_IN} A={A_OUT} gamma={GAMMA} batch={B}/GPU double-DQN, every {TERMINAL_EVERY}th terminal'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1408.1), d.get('bf16_tflops', 1664.5), d.get('hbm_gbs', 6446.3), 'measured'
+    return 1400.0, 1590.0, 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': max(pw) if pw else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle port of train.train on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_steps(steps, warmup, B=CPU_SAMPLE_B):
+    import torch
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import synth
+    from tests.gpu_checks import batch_tensors
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pol = O.make_state(C_IN, A_OUT, 0, perturb=False)
+    tgt = O.clone_state(pol)
+    mom = None
+    ts = []
+    for i in range(warmup + steps):
+        batch = synth.synth_batch(B, C_IN, A_OUT, 1234 + i, terminal_every=8)
+        t0 = time.perf_counter()
+        r = O.dqn_step(pol, tgt, mom, *batch_tensors(batch), discount=GAMMA)
+        mom = r['momentum']
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return B * len(ts) / total, total / len(ts), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    v, per_step, cores = cpu_steps(steps, warmup)
+    sample = (f'{steps} timed + {warmup} warm-up steps of batch {CPU_SAMPLE_B} (same network C={C_IN} A={A_OUT}, double-DQN; '
+              f'CPU samples/s is flat in batch size, BASELINE.md §2), torch CPU fp32, {cores} threads')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': {'workload': workload_name(args.batch), 'cpu_sample_batch': CPU_SAMPLE_B},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_simq(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from spatial_intention_maps_b200 import _lib, networks, synth, train as T
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    if args.gpus > 1 and world == 1:
+        raise SystemExit('for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch
+    torch.manual_seed(0)
+    pol = networks.FCN(C_IN, A_OUT, max_batch=B).to(dev).train()
+    tgt = networks.FCN(C_IN, A_OUT, max_batch=B)
+    tgt.load_state_dict(pol.state_dict())
+    tgt = tgt.to(dev).eval()
+    if world > 1:                                    # identical replicas
+        dist.broadcast(pol.flat_params, 0); dist.broadcast(tgt.flat_params, 0)
+    opt = torch.optim.SGD(pol.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    batch = synth.synth_batch(B, C_IN, A_OUT, 1234 + rank, terminal_every=TERMINAL_EVERY)
+    hb = T.HostBatch(B, C_IN).fill(batch)
+    db = T.DeviceBatch(B, C_IN, dev).upload(hb)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        T.train_step_device(pol, tgt, opt, db, B, GAMMA, 100, True)
+
+    def step_e2e():
+        db.upload(hb)
+        T.train_step_device(pol, tgt, opt, db, B, GAMMA, 100, True)
+        db.out2_host.copy_(db.out2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(db.out2_host[0])
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    # ---- device-resident throughput + per-kernel-class event timing ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pol.ctx(B).launches()
+    L.simq_profile(1, None, None, None)
+    ms_dev = timed(step_device, args.steps)
+    pm, pf, pl = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+    L.simq_profile(0, pm, pf, pl)
+    launches = pol.ctx(B).launches() - launches0
+    # ---- end to end through host buffers ----
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    loss = float(db.out2_host[0])
+    # forward+backward only (the literal BASELINE.json wording), informational
+    x = db.s.permute(0, 3, 1, 2)
+
+    def fwd_bwd():
+        opt.zero_grad(set_to_none=True)
+        q = pol(x)
+        q.backward(q_grad)
+    q_grad = torch.zeros((B, A_OUT, 96, 96), device=dev)
+    q_grad.view(B, -1)[:, 7] = 1.0 / B
+    fwd_bwd()
+    ms_fb = timed(fwd_bwd, max(2, args.steps // 2)) / max(2, args.steps // 2)
+
+    if rank == 0:
+        sustained, burst, hbm, how = peaks()
+        conv_tf = (pf[0] / (pm[0] * 1e-3)) / 1e12 if pm[0] > 0 else 0.0
+        wgrad_tf = (pf[1] / (pm[1] * 1e-3)) / 1e12 if pm[1] > 0 else 0.0
+        per_step = ms_dev / args.steps
+        value = world * B * args.steps / (ms_dev * 1e-3)
+        e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x2-split operands (hi+lo, 3 tcgen05 MMAs per product), f32 accumulate/activations-in-f32-precision',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(B), 'global_batch': world * B, 'parallelism': f'dp{world}',
+                       'l2': 'no flush: a step streams >3 GB of activations per GPU through the 126 MB L2, evicting the 47 MB batch',
+                       'step_gflop_per_sample': STEP_GFLOP},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': hb.h2d_bytes(), 'd2h_bytes_per_step': 8,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (tcgen05 3x3/1x1 conv + dgrad)', 'achieved': conv_tf, 'peak': sustained / 1.0,
+                         'unit': 'TFLOP/s', 'frac': conv_tf / sustained, 'traffic': None, 'peak_source': f'{how} bf16 sustained',
+                         'launches': int(pl[0]), 'ms_per_step_in_kernel': pm[0] / args.steps,
+                         'share_of_step': (pm[0] / args.steps) / per_step,
+                         'note': 'algorithmic FLOPs (2*valid_pixels*N*K*taps); the kernel issues 3 bf16 MMAs per product over 625/576 padded rows, '
+                                 'so issued tensor work = 3.26x algorithmic: issued_frac = frac*3.26',
+                         'issued_frac': conv_tf * 3 * 625 / 576 / sustained,
+                         'wgrad_kernel': {'achieved': wgrad_tf, 'frac': wgrad_tf / sustained, 'launches': int(pl[1]),
+                                          'ms_per_step_in_kernel': pm[1] / args.steps}},
+            'step_tflops_algorithmic': STEP_GFLOP * 1e-3 * value,
+            'fwd_bwd_only': {'value': world * B / (ms_fb * 1e-3), 'unit': UNIT, 'ms': ms_fb},
+            'clocks': clocks, 'loss': loss,
+        }
+        if world == 1 and not args.no_cpu:
+            v, per, cores = cpu_steps(3, 1)
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': f'3 timed + 1 warm-up steps of batch {CPU_SAMPLE_B} of the same step (oracle port of train.train, torch CPU fp32)'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='simq', choices=['simq', 'reference'])
+    ap.add_argument('--batch', type=int, default=128, help='per-GPU minibatch')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_simq(args)
+
+
+if __name__ == '__main__':
+    main()

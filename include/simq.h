@@ -102,6 +102,12 @@ int simq_greedy_action(simq_ctx*, const float* params, const float* bn, const fl
 /* How many of this library's kernels were launched through this ctx so far. */
 int64_t simq_launch_count(const simq_ctx*);
 
+/* Per-kernel-class device timing for bench.py's roofline.  Collects what was recorded since the last
+ * call into ms / flops / launches (arrays of 2: [0] tcgen05 conv+dgrad kernel, [1] tcgen05 wgrad
+ * kernel incl. its split reduction; any may be NULL to discard), then enables or disables recording
+ * (CUDA events around every launch of those classes, on the launching stream). */
+int simq_profile(int enable, double* ms, double* flops, long long* launches);
+
 /* ---- test hooks (exercise single kernels through the C-ABI; used by tests/ only) ---- */
 /* Copy an internal activation of the last forward (set 0 = saved set, 1 = scratch set) as dense
  * NCHW f32.  id: see simq_debug_tensor_name(). Returns channels*H*W per sample through *chw. */

@@ -113,8 +113,12 @@ def make_state(C: int, A: int, seed: int = 0, perturb: bool = True) -> "OrderedD
     return st
 
 
-def clone_state(st):
-    return OrderedDict((k, v.clone()) for k, v in st.items())
+def clone_state(st, dtype=None):
+    """Deep copy; ``dtype=torch.float64`` gives the double-precision twin used to measure how far
+    the fp32 reference itself is from the exact result (gradients are ill-conditioned: ReLU / max-pool
+    mask flips under rounding noise dominate their error)."""
+    return OrderedDict((k, (v.to(dtype) if (dtype is not None and v.is_floating_point()) else v.clone()))
+                       for k, v in st.items())
 
 
 # --------------------------------------------------------------------------------------
@@ -228,7 +232,7 @@ def dqn_step(policy, target, momentum: Optional[Dict[str, torch.Tensor]],
     step (torch.optim.SGD: buf = g on first step).  Returns dict with loss, td_error, grads,
     grad_norm, q (online Q-map on ``state``), best_action, momentum."""
     B = state.shape[0]
-    names = [n for n in policy if policy[n].dtype == torch.float32 and policy[n].dim() >= 1
+    names = [n for n in policy if policy[n].is_floating_point() and policy[n].dim() >= 1
              and not n.endswith(('running_mean', 'running_var')) and not n.startswith('resnet18.fc.')]
     leaves = {}
     work = OrderedDict(policy)            # shallow: buffers shared (mutated), params replaced by leaves
@@ -238,7 +242,7 @@ def dqn_step(policy, target, momentum: Optional[Dict[str, torch.Tensor]],
 
     output = forward(work, state, True)                                            # :114
     q_sa = output.view(B, -1).gather(1, action.view(B, 1)).squeeze(1)              # :115
-    next_v = torch.zeros(B, dtype=torch.float32)                                   # :116
+    next_v = torch.zeros(B, dtype=state.dtype)                                     # :116
     best = torch.zeros(0, dtype=torch.long)
     with torch.no_grad():
         if next_state.shape[0] > 0:
@@ -255,7 +259,7 @@ def dqn_step(policy, target, momentum: Optional[Dict[str, torch.Tensor]],
     grads_t = torch.autograd.grad(loss, [leaves[n] for n in names])                # :131-132
     grads = OrderedDict((n, g.detach().clone()) for n, g in zip(names, grads_t))
 
-    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).to(state.dtype)
     if grad_clip is not None:                                                      # :133-134
         coef = min(1.0, float(grad_clip) / (float(total_norm) + 1e-6))
         if coef < 1.0:

@@ -22,6 +22,43 @@ extern "C" const char* simq_last_error(void) { return g_err; }
 extern "C" int simq_version(void) { return 1; }
 
 // ------------------------------------------------------------------------------------------------
+// per-kernel-class timing with CUDA events on the launching stream
+// ------------------------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+void prof_enable(bool on) { g_prof_on = on; }
+void prof_mark(int cls, bool begin, double flops, cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    if (begin) { ProfRec r; r.e0 = e; r.e1 = nullptr; r.cls = cls; r.flops = flops; g_prof.push_back(r); }
+    else if (!g_prof.empty()) g_prof.back().e1 = e;
+}
+int prof_collect(double* ms, double* flops, long long* launches) {
+    for (int i = 0; i < PROF_CLASSES; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+    for (auto& r : g_prof) {
+        if (!r.e1) { g_prof_pool.push_back(r.e0); continue; }
+        float t = 0;
+        SIMQ_CUDA(cudaEventSynchronize(r.e1));
+        SIMQ_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1;
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof.clear();
+    return 0;
+}
+extern "C" int simq_profile(int enable, double* ms, double* flops, long long* launches) {
+    int rc = 0;
+    if (ms && flops && launches) rc = prof_collect(ms, flops, launches);
+    prof_enable(enable != 0);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // network description: the 70 trainable tensors / 22 BatchNorms of networks.FCN in state_dict order
 // ------------------------------------------------------------------------------------------------
 struct ConvP { int w; int cin, cout, k; };        // index of the weight in the param list

@@ -435,7 +435,11 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
         make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
         return 1;
     dim3 grid(ceil_div(A.rows, UM_BM), N / BN);
+    // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
+    const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
     conv_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, A.rows, A.cols, N, ntaps, out, ep);
+    prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
@@ -480,11 +484,13 @@ static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, fl
     if (per_split * nsplit > umma_wgrad_scratch_floats()) { simq_set_error("wgrad scratch too small"); return 1; }
     long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(ceil_div(Cout, UM_BM), Cin / BN, ntaps * nsplit);
+    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s);
     wgrad_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk,
                                                                   scratch);
     SIMQ_LAUNCH_CHECK();
     long long n = (long long)per_split;
     wgrad_reduce_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scratch, Cout, Cin, ntaps, nsplit, dW);
+    prof_mark(PROF_WGRAD, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }

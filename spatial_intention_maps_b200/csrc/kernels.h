@@ -92,3 +92,9 @@ int umma_init();             // resolves cuTensorMapEncodeTiled
 bool umma_conv_supported(int K, int N);
 bool umma_wgrad_supported(int Cout, int Cin);
 size_t umma_wgrad_scratch_floats();
+
+// ---- per-kernel-class device timing (bench.py's roofline): CUDA events around the launches of a class ----
+enum { PROF_CONV = 0, PROF_WGRAD = 1, PROF_CLASSES = 2 };
+void prof_enable(bool on);
+void prof_mark(int cls, bool begin, double flops, cudaStream_t s);
+int prof_collect(double* ms, double* flops, long long* launches);      // syncs the recorded events; arrays [PROF_CLASSES]

@@ -157,7 +157,7 @@ class Cfg:
         self.final_exploration, self.checkpoint_path, self.policy_path = 0.01, None, None
 
 
-def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True):
+def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False):
     """nsteps updates on the GPU (fused simq_train_step, or the autograd path with a stock SGD exactly as
     the reference's train.py drives it) and in the oracle.  Returns a dict of error metrics."""
     pol, st = make_net(Cin, A, seed, max_batch=B, backend=backend)
@@ -172,6 +172,10 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
     names = O.trainable_names(Cin, A)
     for step in range(nsteps):
         batch = synth.synth_batch(B, Cin, A, seed + 1000 * step, terminal_every=terminal_every)
+        if step == 0 and with_fp64:        # double-precision twin of the reference: the yardstick for gradients
+            s_, a_, r_, ns_, m_ = batch_tensors(batch)
+            r64 = O.dqn_step(O.clone_state(st, torch.float64), O.clone_state(st, torch.float64), None, s_.double(), a_,
+                             r_.double(), ns_.double(), m_, discount=gamma, apply_update=False)
         r = O.dqn_step(o_pol, o_tgt, o_mom, *batch_tensors(batch), discount=gamma)
         o_mom = r['momentum']
         if fused:
@@ -188,6 +192,16 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
             out['grad_rel_l2'] = {n: rel_l2(gmap[n], r['grads'][n]) for n in names}
             gn = float(torch.sqrt(sum((gmap[n].double() ** 2).sum() for n in names)))
             out['grad_norm'], out['grad_norm_ref'] = gn, r['grad_norm'] * min(1.0, 100.0 / (r['grad_norm'] + 1e-6))
+            flat = lambda d: torch.cat([d[n].detach().double().cpu().reshape(-1) for n in names])
+            out['flat_grad_rel_l2'] = rel_l2(flat(gmap), flat(r['grads']))
+            out['grad_abs'] = {n: float((gmap[n].double().cpu() - r['grads'][n].double()).abs().max()) for n in names}
+            out['grad_ref_norm'] = {n: float(r['grads'][n].double().norm()) for n in names}
+            if with_fp64:
+                out['grad_rel_l2_64'] = {n: rel_l2(gmap[n], r64['grads'][n]) for n in names}
+                out['ref32_rel_l2_64'] = {n: rel_l2(r['grads'][n], r64['grads'][n]) for n in names}
+                out['flat_grad_rel_l2_64'] = rel_l2(flat(gmap), flat(r64['grads']))
+                out['flat_ref32_rel_l2_64'] = rel_l2(flat(r['grads']), flat(r64['grads']))
+                out['loss_64'] = r64['loss']
     sd = pol.state_dict()
     out['param_rel_l2'] = {n: rel_l2(sd[n], o_pol[n]) for n in names}
     out['bn_err'] = max(float((sd[n].cpu() - o_pol[n]).abs().max() / (o_pol[n].abs().max() + 1e-6))
