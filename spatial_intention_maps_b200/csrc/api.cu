@@ -116,7 +116,7 @@ extern "C" int simq_layout(int C, int A, int64_t* n_params, int64_t* n_bn, int64
 // context
 // ------------------------------------------------------------------------------------------------
 struct ActSet {
-    float* raw0; Split a0;
+    float* raw0; Split a0; Split acol;       // acol: im2col of the stem input [B*2304][Kp]
     struct { float *raw1, *raw2, *rawd; Split b1, out; } blk[8];
     float* raw_h1; Split u1; float* raw_h2; float* t;
     float* bnstat;                   // [22][4][MAX_CH] : mean, invstd, scale, shift
@@ -125,6 +125,7 @@ struct ActSet {
 
 struct PackedSet {                   // split-bf16 shadows of the conv weights of one parameter vector
     Split fwd[21], bwd[21];          // 16 3x3 + 3 downsample + head conv1 + head conv2, in network order
+    Split stem;                      // resnet18.conv1 as [64][Kp]
     const float* key; uint64_t version; bool used;
 };
 
@@ -137,7 +138,7 @@ struct simq_ctx {
     // scratch
     float* partials; float* sums; double* dpartials;
     float *G[2], *g_mid, *du1, *dt, *dz0, *dy0, *hp, *wscratch, *stem_partials;
-    Split dyA, dyB, dy2h;
+    Split dyA, dyB, dy2h, dy0s; float* stem_tmp;
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     long long launches0;
 };
@@ -174,6 +175,7 @@ static void carve_all(simq_ctx* c, bool dry) {
         ActSet& S = c->set[s];
         S.raw0 = carve<float>(c, R48 * 64, dry);
         S.a0 = carve_split(c, R25 * 64, dry);
+        S.acol = carve_split(c, R48 * stem_kp(d.C), dry);
         for (int b = 0; b < 8; ++b) {
             size_t n = R25 * d.blk[b].planes;
             S.blk[b].raw1 = carve<float>(c, n, dry);
@@ -196,10 +198,14 @@ static void carve_all(simq_ctx* c, bool dry) {
             c->packed[p].fwd[i] = carve_split(c, n, dry);
             c->packed[p].bwd[i] = carve_split(c, n, dry);
         }
+        c->packed[p].stem = carve_split(c, (size_t)64 * stem_kp(d.C), dry);
         c->packed[p].key = nullptr; c->packed[p].version = 0; c->packed[p].used = false;
     }
     c->packed_next = 0;
-    c->partials = carve<float>(c, (size_t)STAT_BLOCKS * 3 * MAX_CH, dry);
+    {
+        size_t need = (size_t)STAT_BLOCKS * 3 * MAX_CH, conv_need = (size_t)umma_conv_m_tiles((long long)R48) * 2 * MAX_CH;
+        c->partials = carve<float>(c, need > conv_need ? need : conv_need, dry);
+    }
     c->sums = carve<float>(c, 3 * MAX_CH, dry);
     c->dpartials = carve<double>(c, 1024, dry);
     c->G[0] = carve<float>(c, R25 * 512, dry);
@@ -215,6 +221,8 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->dyA = carve_split(c, R25 * 512, dry);
     c->dyB = carve_split(c, R25 * 512, dry);
     c->dy2h = carve_split(c, R48 * 32, dry);
+    c->dy0s = carve_split(c, R48 * 64, dry);
+    c->stem_tmp = carve<float>(c, (size_t)64 * stem_kp(d.C), dry);
     c->q_s = carve<float>(c, B * 2 * 9216, dry);
     c->q_no = carve<float>(c, B * 2 * 9216, dry);
     c->q_nt = carve<float>(c, B * 2 * 9216, dry);
@@ -300,15 +308,17 @@ static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version,
         if (k_pack_weights(params + c->d.poff[convs[i].w], convs[i].cout, convs[i].cin, convs[i].k * convs[i].k, ps->fwd[i],
                            ps->bwd[i], s)) { *err = 1; return nullptr; }
     }
+    if (k_pack_stem(params + c->d.poff[c->d.stem.w], c->d.C, stem_kp(c->d.C), ps->stem, s)) { *err = 1; return nullptr; }
     ps->key = params; ps->version = version; ps->used = true;
     return ps;
 }
 
 #define TRY(expr) do { if (expr) return 1; } while (0)
 
-// BatchNorm forward bookkeeping for one BN: fills mean/invstd/scale/shift of set S
+// BatchNorm forward bookkeeping for one BN: fills mean/invstd/scale/shift of set S.
+// nparts > 0: the conv epilogue already left `nparts` partial rows in c->partials; 0: reduce `raw` here.
 static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, long long rows, double count, const float* params,
-                      float* bn, int64_t* nbt, int bias_param, int training, cudaStream_t s) {
+                      float* bn, int64_t* nbt, int bias_param, int training, int nparts, cudaStream_t s) {
     const NetDesc& d = c->d;
     const float* gamma = params + d.poff[b.gamma];
     const float* beta = params + d.poff[b.gamma + 1];
@@ -316,14 +326,26 @@ static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, lo
     float* rmean = bn + d.bnoff[b.idx];
     float* rvar = rmean + b.ch;
     if (training) {
-        TRY(k_colstats(raw, rows, b.ch, c->partials, s));
-        TRY(k_bn_finalize_train(c->partials, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
+        if (nparts == 0) { TRY(k_colstats(raw, rows, b.ch, c->partials, s)); nparts = STAT_BLOCKS; }
+        TRY(k_bn_finalize_train(c->partials, nparts, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
                                 bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), bnstat(S, b.idx, BS_SCALE),
                                 bnstat(S, b.idx, BS_SHIFT), s));
     } else {
         TRY(k_bn_eval_affine(b.ch, gamma, beta, bias, rmean, rvar, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT), s));
     }
     return 0;
+}
+
+// conv -> BatchNorm statistics of its raw output.  With the tcgen05 back-end in training mode the conv
+// epilogue emits the per-tile column sums itself (no extra pass over the raw output).
+static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Split W, int N, int ntaps, float* raw, int pitch25,
+                   const BnP& b, double count, const float* params, float* bn, int64_t* nbt, int bias_param, int training,
+                   cudaStream_t s) {
+    ConvEpilogue ep = conv_ep(pitch25);
+    int nparts = 0;
+    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = c->partials; nparts = umma_conv_m_tiles(rows); }
+    TRY(conv_any(c, c->backend, in, rows, K, W, N, ntaps, raw, ep, s));
+    return bn_prepare(c, S, b, raw, rows, count, params, bn, nbt, bias_param, training, nparts, s);
 }
 
 static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* bn, int64_t* nbt, const float* x, int B,
@@ -334,27 +356,55 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     const int be = c->backend;
     S.valid = false;
     // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
-    TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
-    TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, s));
+    if (be == SIMQ_BACKEND_UMMA) {
+        TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));
+        TRY(conv_bn(c, S, S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, s));
+    } else {
+        TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
+        TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, 0, s));
+    }
     TRY(k_stem_pool(S.raw0, B, bnstat(S, d.stem_bn.idx, BS_SCALE), bnstat(S, d.stem_bn.idx, BS_SHIFT), S.a0, s));
     // residual stages                                            (resnet.py:31-47, 99-102)
     Split in = S.a0;
-    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
     Split none{nullptr, nullptr};
+    const bool fused_eval = !training && be == SIMQ_BACKEND_UMMA;
+    if (fused_eval)                 // eval-mode BN is a per-channel affine known before the conv runs: fold it into the epilogues
+        for (int b = 0; b < 8; ++b) {
+            const BlockP& P = d.blk[b];
+            TRY(bn_prepare(c, S, P.b1, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
+            TRY(bn_prepare(c, S, P.b2, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
+            if (P.has_ds) TRY(bn_prepare(c, S, P.bds, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
+        }
     for (int b = 0; b < 8; ++b) {
         const BlockP& P = d.blk[b];
         auto& A = S.blk[b];
         const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
-        TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[s1], P.planes, 9, A.raw1, ep25, s));
-        TRY(bn_prepare(c, S, P.b1, A.raw1, R25, cnt24, params, bn, nbt, -1, training, s));
+        if (fused_eval) {
+            // conv1 -> BN -> ReLU -> split activation in one kernel; conv2 -> BN -> (+identity) -> ReLU likewise
+            ConvEpilogue e1 = conv_ep(1);
+            e1.scale = bnstat(S, P.b1.idx, BS_SCALE); e1.shift = bnstat(S, P.b1.idx, BS_SHIFT); e1.relu = 1; e1.out_split = A.b1;
+            TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[s1], P.planes, 9, nullptr, e1, s));
+            ConvEpilogue e2 = conv_ep(1);
+            e2.scale = bnstat(S, P.b2.idx, BS_SCALE); e2.shift = bnstat(S, P.b2.idx, BS_SHIFT); e2.relu = 1; e2.out_split = A.out;
+            if (P.has_ds) {
+                ConvEpilogue ed = conv_ep(1);
+                ed.scale = bnstat(S, P.bds.idx, BS_SCALE); ed.shift = bnstat(S, P.bds.idx, BS_SHIFT);
+                TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[conv_slot(d, P.ds.w)], P.planes, 1, A.rawd, ed, s));
+                e2.add_prev = A.rawd;
+            } else {
+                e2.res = in;
+            }
+            TRY(conv_any(c, be, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, nullptr, e2, s));
+            in = A.out;
+            continue;
+        }
+        TRY(conv_bn(c, S, in, R25, P.cin, pw->fwd[s1], P.planes, 9, A.raw1, 1, P.b1, cnt24, params, bn, nbt, -1, training, s));
         TRY(k_bn_apply(A.raw1, R25, P.planes, bnstat(S, P.b1.idx, BS_SCALE), bnstat(S, P.b1.idx, BS_SHIFT), 0, none, nullptr,
                        nullptr, nullptr, 1, A.b1, s));
-        TRY(conv_any(c, be, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, A.raw2, ep25, s));
-        TRY(bn_prepare(c, S, P.b2, A.raw2, R25, cnt24, params, bn, nbt, -1, training, s));
+        TRY(conv_bn(c, S, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, A.raw2, 1, P.b2, cnt24, params, bn, nbt, -1, training, s));
         if (P.has_ds) {
-            const int sd = conv_slot(d, P.ds.w);
-            TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[sd], P.planes, 1, A.rawd, ep25, s));
-            TRY(bn_prepare(c, S, P.bds, A.rawd, R25, cnt24, params, bn, nbt, -1, training, s));
+            TRY(conv_bn(c, S, in, R25, P.cin, pw->fwd[conv_slot(d, P.ds.w)], P.planes, 1, A.rawd, 1, P.bds, cnt24, params, bn, nbt, -1,
+                        training, s));
             TRY(k_bn_apply(A.raw2, R25, P.planes, bnstat(S, P.b2.idx, BS_SCALE), bnstat(S, P.b2.idx, BS_SHIFT), 2, none, A.rawd,
                            bnstat(S, P.bds.idx, BS_SCALE), bnstat(S, P.bds.idx, BS_SHIFT), 1, A.out, s));
         } else {
@@ -364,12 +414,11 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
         in = A.out;
     }
     // head                                                       (networks.py:18-26)
-    TRY(conv_any(c, be, in, R25, 512, pw->fwd[conv_slot(d, d.h1.w)], 128, 1, S.raw_h1, ep25, s));
-    TRY(bn_prepare(c, S, d.hbn1, S.raw_h1, R25, cnt24, params, bn, nbt, d.h1_bias, training, s));
+    TRY(conv_bn(c, S, in, R25, 512, pw->fwd[conv_slot(d, d.h1.w)], 128, 1, S.raw_h1, 1, d.hbn1, cnt24, params, bn, nbt, d.h1_bias,
+                training, s));
     TRY(k_head_up1(S.raw_h1, B, bnstat(S, d.hbn1.idx, BS_SCALE), bnstat(S, d.hbn1.idx, BS_SHIFT), S.u1, s));
-    ConvEpilogue ep0{0, nullptr, nullptr, nullptr};
-    TRY(conv_any(c, be, S.u1, R48, 128, pw->fwd[conv_slot(d, d.h2.w)], 32, 1, S.raw_h2, ep0, s));
-    TRY(bn_prepare(c, S, d.hbn2, S.raw_h2, R48, cnt48, params, bn, nbt, d.h2_bias, training, s));
+    TRY(conv_bn(c, S, S.u1, R48, 128, pw->fwd[conv_slot(d, d.h2.w)], 32, 1, S.raw_h2, 0, d.hbn2, cnt48, params, bn, nbt, d.h2_bias,
+                training, s));
     TRY(k_head_t(S.raw_h2, R48, bnstat(S, d.hbn2.idx, BS_SCALE), bnstat(S, d.hbn2.idx, BS_SHIFT), params + d.poff[d.h3.w], d.A,
                  S.t, s));
     if (q) TRY(k_head_up2(S.t, B, d.A, params + d.poff[d.h3_bias], q, s));
@@ -442,7 +491,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                       bnstat(S, hb2, BS_INVSTD), params + d.poff[d.h3.w], c->sums, cnt48, c->dy2h, s));
     TRY(bias_grad(c, c->dy2h, R48, 32, grads + d.poff[d.h2_bias], s));
     TRY(wgrad_any(c, be, c->dy2h, S.u1, R48, 32, 128, 1, grads + d.poff[d.h2.w], s));
-    ConvEpilogue ep0{0, nullptr, nullptr, nullptr};
+    ConvEpilogue ep0 = conv_ep(0);
     TRY(conv_any(c, be, c->dy2h, R48, 32, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, s));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     float* G = c->G[0];
@@ -451,7 +500,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr, none, s));
     TRY(bias_grad(c, c->dyA, R25, 128, grads + d.poff[d.h1_bias], s));
     TRY(wgrad_any(c, be, c->dyA, S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w], s));
-    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
+    ConvEpilogue ep25 = conv_ep(1);
     TRY(conv_any(c, be, c->dyA, R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, ep25, s));
     { float* t = G; G = Gn; Gn = t; }
     // ---- residual stages, last to first ----
@@ -483,8 +532,14 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     // ---- stem: maxpool + ReLU + BN + conv 7x7 ----
     const int sb = d.stem_bn.idx;
     TRY(k_pool_bwd(G, S.raw0, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
-    TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, s));
-    TRY(k_stem_wgrad(x, x_layout, B, d.C, c->dy0, c->stem_partials, grads + d.poff[d.stem.w], s));
+    if (be == SIMQ_BACKEND_UMMA) {
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, s));
+        TRY(wgrad_any(c, be, c->dy0s, S.acol, R48, 64, stem_kp(d.C), 1, c->stem_tmp, s));
+        TRY(k_strip_stem(c->stem_tmp, d.C, stem_kp(d.C), grads + d.poff[d.stem.w], s));
+    } else {
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, s));
+        TRY(k_stem_wgrad(x, x_layout, B, d.C, c->dy0, c->stem_partials, grads + d.poff[d.stem.w], s));
+    }
     return 0;
 }
 
@@ -622,7 +677,7 @@ extern "C" int simq_test_conv(simq_ctx* c, int backend, int mode, int B, int Cin
     Split wf = c->packed[1].fwd[15], wb = c->packed[1].bwd[15];       // layer4.1.conv2 slot: 512*512*9 elements
     c->packed[1].used = false;
     Split none{nullptr, nullptr};
-    ConvEpilogue ep25{1, nullptr, nullptr, nullptr};
+    ConvEpilogue ep25 = conv_ep(1);
     if (mode == 0) {
         TRY(k_import_p25(a, B, Cin, X, nullptr, s));
         TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));

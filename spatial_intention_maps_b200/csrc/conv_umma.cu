@@ -120,45 +120,60 @@ __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 
 #define UM_BK 64
 #define UM_THREADS 192          // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+#define EPI_LD 36               // floats per staged row (32 + 4 pad: conflict-free float4 row writes and column reads)
+
 template <int BN>
 struct ConvCfg {
     static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // one plane of the A tile (16 KB)
     static constexpr int W_BYTES = BN * UM_BK * 2;            // one plane of the W tile
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4; // per epilogue warp: 32 rows x 32 columns fp32
+    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares
+    static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - FIXED) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+    static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward conv / dgrad
+// forward conv / dgrad: persistent CTAs (one per SM) walk the (m_tile, n_tile) list; the accumulator is
+// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // ------------------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, long long rows, int K,
-                 int N, int ntaps, float* __restrict__ out, ConvEpilogue ep) {
+                 int N, int ntaps, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
     using Cfg = ConvCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;       // full[s], empty[s], accum, tmem slot
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    float* staging = reinterpret_cast<float*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* csum = reinterpret_cast<float*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + Cfg::CSUM_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * Cfg::STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m0 = (long long)blockIdx.x * UM_BM;
-    const int n0 = blockIdx.y * BN;
     const int kchunks = K / UM_BK;
     const int iters = ntaps * kchunks;
+    const int total_tiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&mAhi); tma_prefetch_desc(&mAlo); tma_prefetch_desc(&mWhi); tma_prefetch_desc(&mWlo);
     }
-    if (warp == 1) tmem_alloc<tmem_cols(BN)>(tmem_slot);
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -168,90 +183,149 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                const int t = it / kchunks, kc = it - t * kchunks;
-                const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-                const int arow = (int)(m0 + off);
-                tma_load_2d(sa, &mAhi, full_bar(s), kc * UM_BK, arow);
-                tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * UM_BK, arow);
-                tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * UM_BK, t * N + n0);
-                tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * UM_BK, t * N + n0);
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
+                const long long m0 = (long long)m_t * UM_BM;
+                for (int it = 0; it < iters; ++it) {
+                    const int t = it / kchunks, kc = it - t * kchunks;
+                    const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                    const int arow = (int)(m0 + off);
+                    tma_load_2d(sa, &mAhi, full_bar(s), kc * UM_BK, arow);
+                    tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * UM_BK, arow);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * UM_BK, t * N + n0);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * UM_BK, t * N + n0);
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
             int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(full_bar(s), ph);
+            int acc = 0; uint32_t aph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), aph ^ 1u);           // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < UM_BK / 16; ++k) {
-                    const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
-                    const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
-                    const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
-                    const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
-                    tc_mma_bf16(tmem_base, a_lo, w_hi, idesc, (it | k) != 0);
-                    tc_mma_bf16(tmem_base, a_hi, w_lo, idesc, 1);
-                    tc_mma_bf16(tmem_base, a_hi, w_hi, idesc, 1);
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
+                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
+                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
+                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
+                        tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                        tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
+                        tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                    }
+                    tc_commit(empty_bar(s));            // frees the stage once these MMAs have read it
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(empty_bar(s));            // frees the stage once these MMAs have read it
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
             }
-            tc_commit(accum_bar);
         }
     } else {
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
-        const long long m = m0 + quad * 32 + lane;
-        const bool in_range = m < rows;
-        const bool valid = in_range && !(ep.pitch25 && !p25_valid((int)(m % IMG25)));
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
+        float* stg = staging + quad * 32 * EPI_LD;
+        float* cs = csum + quad * 2 * BN;
+        const int sr = lane >> 3, scol = (lane & 7) * 4;  // store phase: 4 rows per instruction, float4 per lane
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
+            const long long mw = (long long)m_t * UM_BM + quad * 32;   // first row of this warp
+            const long long m = mw + lane;
+            const bool valid = m < rows && !(ep.pitch25 && !p25_valid((int)(m % IMG25)));
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-            if (in_range) {
-                const size_t o = (size_t)m * N + n0 + c;
-                if (!valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                } else {
-                    if (ep.add_prev) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o + i);
-                            v[i] += p.x; v[i + 1] += p.y; v[i + 2] += p.z; v[i + 3] += p.w;
-                        }
-                    }
-                    if (ep.add_g) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            float g[8];
-                            load8(ep.add_g + o + i, g);
-                            bf16x8 mk = *reinterpret_cast<const bf16x8*>(ep.add_g_mask + o + i);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (bf2f(mk.v[j]) > 0.f) v[i + j] += g[j];
-                        }
-                    }
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (c + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(out + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 32; i += 4) {
+                    float4 w4 = valid ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = w4;
+                }
+                __syncwarp();
+                if (ep.stats) {                         // lane = column: sums over this warp's 32 rows
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) { float x = stg[r * EPI_LD + lane]; s1 += x; s2 = fmaf(x, x, s2); }
+                    cs[c + lane] = s1; cs[BN + c + lane] = s2;
+                }
+                const int n = n0 + c + scol;
+                float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.scale) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + sr;
+                    const long long mr = mw + r;
+                    if (mr >= rows) continue;
+                    const bool rvalid = !(ep.pitch25 && !p25_valid((int)(mr % IMG25)));
+                    float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + scol);
+                    const size_t o = (size_t)mr * N + n;
+                    if (rvalid) {
+                        if (ep.scale) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
+                        if (ep.add_prev) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
+                        if (ep.res.hi) {
+                            uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
+                            const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
+                            x.x += bf2f(hb[0]) + bf2f(lb[0]); x.y += bf2f(hb[1]) + bf2f(lb[1]);
+                            x.z += bf2f(hb[2]) + bf2f(lb[2]); x.w += bf2f(hb[3]) + bf2f(lb[3]);
+                        }
+                        if (ep.add_g) {
+                            float4 g = *reinterpret_cast<const float4*>(ep.add_g + o);
+                            uint2 mk = *reinterpret_cast<const uint2*>(ep.add_g_mask + o);
+                            const bf16* mb = reinterpret_cast<const bf16*>(&mk);
+                            if (bf2f(mb[0]) > 0.f) x.x += g.x;
+                            if (bf2f(mb[1]) > 0.f) x.y += g.y;
+                            if (bf2f(mb[2]) > 0.f) x.z += g.z;
+                            if (bf2f(mb[3]) > 0.f) x.w += g.w;
+                        }
+                        if (ep.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    } else {
+                        x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (out) *reinterpret_cast<float4*>(out + o) = x;
+                    if (ep.out_split.hi) {
+                        bf16 h[4], l[4];
+                        split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
+                        *reinterpret_cast<uint2*>(ep.out_split.hi + o) = *reinterpret_cast<const uint2*>(h);
+                        *reinterpret_cast<uint2*>(ep.out_split.lo + o) = *reinterpret_cast<const uint2*>(l);
+                    }
+                }
+                __syncwarp();                           // staging is rewritten by the next chunk
             }
+            if (ep.stats) {                             // combine the 4 warps in a fixed order -> one partial row per m_tile
+                epi_bar_sync();
+                const int t = threadIdx.x - 64;         // 0..127
+                for (int j = t; j < 2 * BN; j += 128) {
+                    float tot = csum[j] + csum[2 * BN + j] + csum[4 * BN + j] + csum[6 * BN + j];
+                    const int which = j / BN, col = j - which * BN;
+                    ep.stats[((size_t)m_t * 2 + which) * N + n0 + col] = tot;
+                }
+                epi_bar_sync();
+            }
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<tmem_cols(BN)>(tmem_base);
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -422,6 +496,8 @@ static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, i
     return 0;
 }
 
+static int g_num_sms = 0;
+
 template <int BN>
 static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     using Cfg = ConvCfg<BN>;
@@ -430,20 +506,27 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
         SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr = true;
     }
+    if (!g_num_sms) {
+        int dev = 0;
+        SIMQ_CUDA(cudaGetDevice(&dev));
+        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
         make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
         return 1;
-    dim3 grid(ceil_div(A.rows, UM_BM), N / BN);
+    const int m_tiles = ceil_div(A.rows, UM_BM), n_tiles = N / BN;
+    const int grid = m_tiles * n_tiles < g_num_sms ? m_tiles * n_tiles : g_num_sms;
     // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
-    conv_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, A.rows, A.cols, N, ntaps, out, ep);
+    conv_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
 
+int umma_conv_m_tiles(long long rows) { return ceil_div(rows, UM_BM); }
 bool umma_conv_supported(int K, int N) { return K % UM_BK == 0 && (N == 32 || N % 64 == 0); }
 bool umma_wgrad_supported(int Cout, int Cin) { return Cout % 64 == 0 && Cin % 64 == 0; }
 

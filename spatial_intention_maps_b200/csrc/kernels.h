@@ -7,7 +7,7 @@
 
 // ---- forward elementwise (kernels_elem.cu) ----
 int k_colstats(const float* x, long long rows, int C, float* partials, cudaStream_t s);
-int k_bn_finalize_train(const float* partials, int C, double count, const float* gamma, const float* beta,
+int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                         const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s);
 int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rmean,
@@ -72,7 +72,20 @@ struct ConvEpilogue {
     const float* add_prev;    // out += add_prev (may alias out)
     const float* add_g;       // out += (mask_hi > 0 ? add_g : 0)  (residual gradient)
     const bf16* add_g_mask;
+    // ---- tcgen05 kernel only (the FMA comparator back-end takes the unfused route) ----
+    const float* scale;       // v = v*scale[n] + shift[n]   (eval-mode BatchNorm folded into the epilogue)
+    const float* shift;
+    Split res;                // v += res.hi + res.lo        (identity shortcut)
+    int relu;
+    Split out_split;          // write v as split bf16 (out may then be NULL)
+    float* stats;             // [m_tiles][2][N] per-tile column sums / sums of squares of the raw accumulators
 };
+static inline ConvEpilogue conv_ep(int pitch25) {
+    ConvEpilogue e;
+    e.pitch25 = pitch25; e.add_prev = nullptr; e.add_g = nullptr; e.add_g_mask = nullptr; e.scale = nullptr; e.shift = nullptr;
+    e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
+    return e;
+}
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
 int k_conv_fma(Split A, long long rows, int K, Split W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
 // dW[co][ci][tap] (OIHW) = sum_p dY[p][co] * X[p+off_tap][ci]   (zero-inits dW itself)
@@ -81,6 +94,11 @@ int k_stem_conv(const float* x, int x_layout, int B, int C, const float* w, floa
 int k_stem_wgrad(const float* x, int x_layout, int B, int C, const float* dy0, float* partials, float* dW,
                  cudaStream_t s);
 size_t stem_wgrad_partial_floats(int C);
+// tensor-core stem: im2col + GEMM (K = 49*C padded to Kp)
+static inline int stem_kp(int C) { return (49 * C + 63) / 64 * 64; }
+int k_stem_im2col(const float* x, int x_layout, int B, int C, int Kp, Split acol, cudaStream_t s);
+int k_pack_stem(const float* w, int C, int Kp, Split out, cudaStream_t s);
+int k_strip_stem(const float* tmp, int C, int Kp, float* dW, cudaStream_t s);
 
 // ---- tcgen05 convolutions (conv_umma.cu) ----
 struct UmmaTensor {          // a split tensor plus its row count / width, enough to build tensor maps
@@ -90,6 +108,7 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
 int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s);
 int umma_init();             // resolves cuTensorMapEncodeTiled
 bool umma_conv_supported(int K, int N);
+int umma_conv_m_tiles(long long rows);     // rows of ConvEpilogue::stats written by k_conv_umma
 bool umma_wgrad_supported(int Cout, int Cin);
 size_t umma_wgrad_scratch_floats();
 

@@ -49,17 +49,27 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
 // nn.BatchNorm2d train-mode bookkeeping (eps 1e-5, momentum 0.1, unbiased var into running_var,
 // num_batches_tracked += 1).  `raw` excludes the conv bias: the batch mean of the true conv output is
 // mean_raw + bias, and the bias cancels in the normalised value.
-__global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int C, double count,
+// One block = 32 channels x 8 partial-row groups (coalesced 128-byte reads of the partial rows); the
+// 8 group sums are combined in a fixed order in shared memory, so the result is deterministic.
+__global__ void __launch_bounds__(256) bn_finalize_train_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          const float* __restrict__ conv_bias, float* rmean, float* rvar,
                                          long long* nbt, float* mean, float* invstd, float* scale, float* shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double sS[8][32], sSS[8][32];
+    const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     double S = 0, SS = 0;
-    for (int b = 0; b < STAT_BLOCKS; ++b) {
-        S += (double)partials[((size_t)b * 2 + 0) * C + c];
-        SS += (double)partials[((size_t)b * 2 + 1) * C + c];
-    }
+    if (c < C)
+        for (int b = r; b < nparts; b += 8) {
+            S += (double)partials[((size_t)b * 2 + 0) * C + c];
+            SS += (double)partials[((size_t)b * 2 + 1) * C + c];
+        }
+    sS[r][cl] = S; sSS[r][cl] = SS;
+    __syncthreads();
+    if (r != 0 || c >= C) return;
+    S = 0; SS = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S += sS[i][cl]; SS += sSS[i][cl]; }
     double m = S / count;
     double var = SS / count - m * m;
     if (var < 0) var = 0;
@@ -77,10 +87,10 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
     if (c == 0 && nbt) nbt[0] += 1;
 }
 
-int k_bn_finalize_train(const float* partials, int C, double count, const float* gamma, const float* beta,
+int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                         const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s) {
-    bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partials, C, count, gamma, beta, conv_bias, rmean, rvar,
+    bn_finalize_train_kernel<<<ceil_div(C, 32), 256, 0, s>>>(partials, nparts, C, count, gamma, beta, conv_bias, rmean, rvar,
                                                               nbt, mean, invstd, scale, shift);
     SIMQ_LAUNCH_CHECK();
     return 0;
@@ -624,16 +634,25 @@ int k_head2_reduce(const float* dt, const float* raw_h2, long long rows, int A, 
     return 0;
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nblk, int K, float* __restrict__ out, float mul) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nblk, int K,
+                                                              float* __restrict__ out, float mul) {
+    __shared__ double sm[8][32];
+    const int kl = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kl;
     double t = 0;
-    for (int b = 0; b < nblk; ++b) t += (double)partials[(size_t)b * K + k];
+    if (k < K)
+        for (int b = r; b < nblk; b += 8) t += (double)partials[(size_t)b * K + k];
+    sm[r][kl] = t;
+    __syncthreads();
+    if (r != 0 || k >= K) return;
+    t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][kl];
     out[k] = (float)(t * (double)mul);
 }
 
 int k_reduce_partials(const float* partials, int nblk, int K, float* out, float mul, cudaStream_t s) {
-    reduce_partials_kernel<<<ceil_div(K, 128), 128, 0, s>>>(partials, nblk, K, out, mul);
+    reduce_partials_kernel<<<ceil_div(K, 32), 256, 0, s>>>(partials, nblk, K, out, mul);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }

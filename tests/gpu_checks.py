@@ -111,6 +111,8 @@ def forward_trace_check(Cin, A, B, seed, training, backend=_lib.BACKEND_UMMA, un
     for name in DEBUG_IDS:
         if name not in ref:
             continue
+        if not training and backend == _lib.BACKEND_UMMA and name.endswith(('.raw1', '.raw2', '.rawd')):
+            continue        # eval mode folds BN into the conv epilogues: the raw conv outputs never materialise
         mine = debug_get(net, name, B, saved=False).view(ref[name].shape)
         errs[name] = relerr(mine, ref[name])
     errs['q'] = relerr(q, ref['q'])
