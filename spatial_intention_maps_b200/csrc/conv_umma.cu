@@ -144,10 +144,13 @@ struct ConvCfg {
 // forward conv / dgrad: persistent CTAs (one per SM) walk the (m_tile, n_tile) list; the accumulator is
 // double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// epilogue feature flags (compile-time: the epilogue is the bottleneck of the short-K layers)
+enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU = 32, EF_F32 = 64, EF_SPLIT = 128 };
+
+template <int BN, int FL>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-                 const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, long long rows, int K,
+                 const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
                  int N, int ntaps, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
     using Cfg = ConvCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -185,14 +188,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
-                const long long m0 = (long long)m_t * UM_BM;
+                const int m0 = m_t * UM_BM;
                 for (int it = 0; it < iters; ++it) {
                     const int t = it / kchunks, kc = it - t * kchunks;
                     const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-                    const int arow = (int)(m0 + off);
+                    const int arow = m0 + off;
                     tma_load_2d(sa, &mAhi, full_bar(s), kc * UM_BK, arow);
                     tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * UM_BK, arow);
                     tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * UM_BK, t * N + n0);
@@ -239,9 +242,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
-            const long long mw = (long long)m_t * UM_BM + quad * 32;   // first row of this warp
-            const long long m = mw + lane;
-            const bool valid = m < rows && !(ep.pitch25 && !p25_valid((int)(m % IMG25)));
+            const int mw = m_t * UM_BM + quad * 32;     // first row of this warp
+            const int m = mw + lane;
+            const bool valid = m < rows && !(ep.pitch25 && !p25_valid(m % IMG25));
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);      // bit r: row mw + r carries data
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
 #pragma unroll 1
@@ -259,7 +263,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = w4;
                 }
                 __syncwarp();
-                if (ep.stats) {                         // lane = column: sums over this warp's 32 rows
+                if (FL & EF_STATS) {                    // lane = column: sums over this warp's 32 rows
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) { float x = stg[r * EPI_LD + lane]; s1 += x; s2 = fmaf(x, x, s2); }
@@ -267,25 +271,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                 }
                 const int n = n0 + c + scol;
                 float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.scale) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
+                if (FL & EF_AFFINE) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
+                const size_t o0 = (size_t)(mw + sr) * N + n;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = i * 4 + sr;
-                    const long long mr = mw + r;
-                    if (mr >= rows) continue;
-                    const bool rvalid = !(ep.pitch25 && !p25_valid((int)(mr % IMG25)));
+                    if (mw + r >= rows) continue;
                     float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + scol);
-                    const size_t o = (size_t)mr * N + n;
-                    if (rvalid) {
-                        if (ep.scale) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
-                        if (ep.add_prev) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
-                        if (ep.res.hi) {
+                    const size_t o = o0 + (size_t)(i * 4) * N;
+                    if ((vmask >> r) & 1u) {
+                        if (FL & EF_AFFINE) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
+                        if (FL & EF_PREV) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
+                        if (FL & EF_RES) {
                             uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
                             const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
                             x.x += bf2f(hb[0]) + bf2f(lb[0]); x.y += bf2f(hb[1]) + bf2f(lb[1]);
                             x.z += bf2f(hb[2]) + bf2f(lb[2]); x.w += bf2f(hb[3]) + bf2f(lb[3]);
                         }
-                        if (ep.add_g) {
+                        if (FL & EF_G) {
                             float4 g = *reinterpret_cast<const float4*>(ep.add_g + o);
                             uint2 mk = *reinterpret_cast<const uint2*>(ep.add_g_mask + o);
                             const bf16* mb = reinterpret_cast<const bf16*>(&mk);
@@ -294,12 +297,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                             if (bf2f(mb[2]) > 0.f) x.z += g.z;
                             if (bf2f(mb[3]) > 0.f) x.w += g.w;
                         }
-                        if (ep.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (FL & EF_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                     } else {
                         x = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (out) *reinterpret_cast<float4*>(out + o) = x;
-                    if (ep.out_split.hi) {
+                    if (FL & EF_F32) *reinterpret_cast<float4*>(out + o) = x;
+                    if (FL & EF_SPLIT) {
                         bf16 h[4], l[4];
                         split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
                         *reinterpret_cast<uint2*>(ep.out_split.hi + o) = *reinterpret_cast<const uint2*>(h);
@@ -308,7 +311,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                 }
                 __syncwarp();                           // staging is rewritten by the next chunk
             }
-            if (ep.stats) {                             // combine the 4 warps in a fixed order -> one partial row per m_tile
+            if (FL & EF_STATS) {                        // combine the 4 warps in a fixed order -> one partial row per m_tile
                 epi_bar_sync();
                 const int t = threadIdx.x - 64;         // 0..127
                 for (int j = t; j < 2 * BN; j += 128) {
@@ -498,12 +501,12 @@ static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, i
 
 static int g_num_sms = 0;
 
-template <int BN>
+template <int BN, int FL>
 static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     using Cfg = ConvCfg<BN>;
     static bool attr = false;
     if (!attr) {
-        SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr = true;
     }
     if (!g_num_sms) {
@@ -511,6 +514,7 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
         SIMQ_CUDA(cudaGetDevice(&dev));
         SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (A.rows >= (1LL << 31) - 256) { simq_set_error("k_conv_umma: too many rows"); return 1; }
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
         make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
@@ -520,10 +524,37 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
     // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
-    conv_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
+    conv_umma_kernel<BN, FL><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
+}
+
+// the epilogue variants the network uses
+template <int BN>
+static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    int fl = 0;
+    if (ep.stats) fl |= EF_STATS;
+    if (ep.scale) fl |= EF_AFFINE;
+    if (ep.add_prev) fl |= EF_PREV;
+    if (ep.res.hi) fl |= EF_RES;
+    if (ep.add_g) fl |= EF_G;
+    if (ep.relu) fl |= EF_RELU;
+    if (out) fl |= EF_F32;
+    if (ep.out_split.hi) fl |= EF_SPLIT;
+    switch (fl) {
+#define CASE(F) case (F): return launch_conv<BN, (F)>(A, W, N, ntaps, out, ep, s)
+        CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
+        CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
+        CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
+        CASE(EF_F32 | EF_G);                                        // dgrad + masked identity gradient
+        CASE(EF_F32 | EF_AFFINE);                                   // eval downsample: BN'd identity
+        CASE(EF_SPLIT | EF_AFFINE | EF_RELU);                       // eval conv1 -> BN -> ReLU
+        CASE(EF_SPLIT | EF_AFFINE | EF_RELU | EF_RES);              // eval conv2 -> BN -> + identity -> ReLU
+        CASE(EF_SPLIT | EF_AFFINE | EF_RELU | EF_PREV);             // eval conv2 -> BN -> + downsample -> ReLU
+#undef CASE
+        default: simq_set_error("k_conv_umma: epilogue combination 0x%x not instantiated", fl); return 1;
+    }
 }
 
 int umma_conv_m_tiles(long long rows) { return ceil_div(rows, UM_BM); }
@@ -536,9 +567,9 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         simq_set_error("k_conv_umma: unsupported shape K=%d N=%d", A.cols, N);
         return 1;
     }
-    if (N == 32) return launch_conv<32>(A, W, N, ntaps, out, ep, s);
-    if (N % 128 == 0) return launch_conv<128>(A, W, N, ntaps, out, ep, s);
-    return launch_conv<64>(A, W, N, ntaps, out, ep, s);
+    if (N == 32) return dispatch_conv<32>(A, W, N, ntaps, out, ep, s);
+    if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
+    return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
 }
 
 size_t umma_wgrad_scratch_floats() { return (size_t)16 << 20; }     // 64 MB

@@ -49,27 +49,38 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
 // nn.BatchNorm2d train-mode bookkeeping (eps 1e-5, momentum 0.1, unbiased var into running_var,
 // num_batches_tracked += 1).  `raw` excludes the conv bias: the batch mean of the true conv output is
 // mean_raw + bias, and the bias cancels in the normalised value.
-// One block = 32 channels x 8 partial-row groups (coalesced 128-byte reads of the partial rows); the
-// 8 group sums are combined in a fixed order in shared memory, so the result is deterministic.
-__global__ void __launch_bounds__(256) bn_finalize_train_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+// One block = 32 channels x 32 partial-row groups (coalesced 128-byte reads of the partial rows, 4 loads in
+// flight per thread: the kernel is latency-bound); the group sums are combined in a fixed order in shared
+// memory, so the result is deterministic.
+__global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          const float* __restrict__ conv_bias, float* rmean, float* rvar,
                                          long long* nbt, float* mean, float* invstd, float* scale, float* shift) {
-    __shared__ double sS[8][32], sSS[8][32];
+    __shared__ double sS[32][33], sSS[32][33];
     const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     double S = 0, SS = 0;
-    if (c < C)
-        for (int b = r; b < nparts; b += 8) {
+    if (c < C) {
+        int b = r;
+        for (; b + 96 < nparts; b += 128) {
+            float a0 = partials[((size_t)b * 2) * C + c], q0 = partials[((size_t)b * 2 + 1) * C + c];
+            float a1 = partials[((size_t)(b + 32) * 2) * C + c], q1 = partials[((size_t)(b + 32) * 2 + 1) * C + c];
+            float a2 = partials[((size_t)(b + 64) * 2) * C + c], q2 = partials[((size_t)(b + 64) * 2 + 1) * C + c];
+            float a3 = partials[((size_t)(b + 96) * 2) * C + c], q3 = partials[((size_t)(b + 96) * 2 + 1) * C + c];
+            S += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+            SS += ((double)q0 + (double)q1) + ((double)q2 + (double)q3);
+        }
+        for (; b < nparts; b += 32) {
             S += (double)partials[((size_t)b * 2 + 0) * C + c];
             SS += (double)partials[((size_t)b * 2 + 1) * C + c];
         }
+    }
     sS[r][cl] = S; sSS[r][cl] = SS;
     __syncthreads();
     if (r != 0 || c >= C) return;
     S = 0; SS = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { S += sS[i][cl]; SS += sSS[i][cl]; }
+    for (int i = 0; i < 32; ++i) { S += sS[i][cl]; SS += sSS[i][cl]; }
     double m = S / count;
     double var = SS / count - m * m;
     if (var < 0) var = 0;
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(256) bn_finalize_train_kernel(const float* __r
 int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                         const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s) {
-    bn_finalize_train_kernel<<<ceil_div(C, 32), 256, 0, s>>>(partials, nparts, C, count, gamma, beta, conv_bias, rmean, rvar,
+    bn_finalize_train_kernel<<<ceil_div(C, 32), 1024, 0, s>>>(partials, nparts, C, count, gamma, beta, conv_bias, rmean, rvar,
                                                               nbt, mean, invstd, scale, shift);
     SIMQ_LAUNCH_CHECK();
     return 0;
