@@ -94,6 +94,25 @@ class DeviceBatch:
         return self
 
 
+def shard_batch(batch, rank: int, world: int):
+    """Rank ``rank``'s contiguous slice of a global replay minibatch (``Transition`` of tuples): the
+    replay sample is drawn with a shared seed on every rank and split along B, no data-path collective."""
+    B = len(batch.state)
+    if B % world:
+        raise ValueError(f'global batch {B} is not divisible by world size {world}')
+    lo, hi = rank * (B // world), (rank + 1) * (B // world)
+    return Transition(*(tuple(f[lo:hi]) for f in batch))
+
+
+def allreduce_mean_(grads: torch.Tensor, out2: torch.Tensor, world: int):
+    """The path's one exchange: sum the flat fp32 gradient vector (and the 2-float loss / td_error
+    report) over ranks, divide by the world size -> gradient of the global-batch mean loss."""
+    dist.all_reduce(grads)
+    grads.mul_(1.0 / world)
+    dist.all_reduce(out2)
+    out2.mul_(1.0 / world)
+
+
 def _momentum_views(net: FCN, optimizer):
     """Make the optimizer's momentum buffers views of the net's flat momentum vector (once)."""
     if net.flat_momentum is None or net.flat_momentum.device != net.flat_params.device:
@@ -137,10 +156,7 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
         _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, float(discount_factor), lr, mom, wd, clip, first,
         1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(db.out2), _lib.stream_ptr()), 'simq_train_step')
     if world > 1:
-        dist.all_reduce(grads)                      # the path's one exchange: flat fp32 gradients, sum
-        grads.mul_(1.0 / world)
-        dist.all_reduce(db.out2)                    # 2 floats: report the global-batch loss / td_error
-        db.out2.mul_(1.0 / world)
+        allreduce_mean_(grads, db.out2, world)
         _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(grads), _lib.ptr(policy.flat_momentum),
                                    lr, mom, wd, clip, first, None, _lib.stream_ptr()), 'simq_sgd_step')
     policy.momentum_initialized = True

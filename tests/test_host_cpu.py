@@ -1,0 +1,120 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/simq.h declares, the flat
+layout matches the reference's state_dict inventory, the host mirror of networks.FCN keeps the
+reference's names / checkpoint format, and the product path refuses to run without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fcn_oracle as O
+from spatial_intention_maps_b200 import _lib, networks, policies, synth, train as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, 'include', 'simq.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(simq_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 15
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), f'{n} declared in include/simq.h but not exported by libsimq.so'
+        assert n in _lib.EXPORTS, f'{n} has no ctypes prototype in _lib.py'
+    assert L.simq_version() >= 1
+
+
+@pytest.mark.parametrize('C,A', [(4, 2), (5, 1), (3, 2), (10, 2)])
+def test_layout_matches_reference_inventory(C, A):
+    n_p, n_b, po, bo = _lib.layout(C, A)
+    spec = O.state_spec(C, A)
+    tr = [(n, s) for n, s, k in spec if k == 'param' and not n.startswith('resnet18.fc.')]
+    assert len(po) == len(tr) + 1 == 71
+    assert [po[i + 1] - po[i] for i in range(70)] == [int(np.prod(s)) for _, s in tr]
+    bns = [s[0] for n, s, k in spec if n.endswith('running_mean')]
+    assert [bo[i + 1] - bo[i] for i in range(22)] == [2 * c for c in bns]
+    assert n_p == po[-1] and n_b == bo[-1]
+
+
+def test_layout_rejects_bad_arguments():
+    assert _lib.lib().simq_layout(0, 2, None, None, None, None) != 0
+    assert b'unsupported' in _lib.lib().simq_last_error()
+    assert _lib.lib().simq_layout(5, 3, None, None, None, None) != 0
+
+
+def test_fcn_state_dict_is_the_reference_format():
+    net = networks.SingleDeviceParallel(networks.FCN(5, 2))
+    sd = net.state_dict()
+    spec = O.state_spec(5, 2)
+    assert list(sd.keys()) == ['module.' + n for n, _, _ in spec] and len(sd) == 138
+    for n, shape, kind in spec:
+        assert tuple(sd['module.' + n].shape) == tuple(shape)
+        assert sd['module.' + n].dtype == (torch.int64 if kind == 'nbt' else torch.float32)
+    st = O.make_state(5, 2, 3)
+    v0 = net.module.params_version
+    net.load_state_dict({'module.' + k: v for k, v in st.items()})
+    assert net.module.params_version != v0                     # the library must re-pack its weight shadows
+    for k, v in st.items():
+        assert torch.equal(net.state_dict()['module.' + k], v)
+    # parameters are views of one flat vector in simq_layout order
+    flat = net.module.flat_params
+    po = net.module._layout[2]
+    for i, (name, p) in enumerate(net.module.trainable()):
+        assert p.data_ptr() == flat.data_ptr() + 4 * po[i]
+        assert torch.equal(flat[po[i]:po[i + 1]].view(p.shape), st[name])
+    assert int(net.module.flat_nbt[0]) == 3 and float(net.module.flat_bn[0]) == float(st['resnet18.bn1.running_mean'][0])
+    # a stock optimizer sees 72 parameters (70 trainable + the never-executed resnet18.fc.*)
+    assert len(list(net.parameters())) == 72
+
+
+def test_init_follows_reference_distributions():
+    torch.manual_seed(0)
+    net = networks.FCN(4, 2)
+    w = net.resnet18.layer3[0].conv1.weight                     # kaiming_normal(fan_out, relu): std = sqrt(2/(256*9))
+    assert abs(float(w.std()) - (2.0 / (256 * 9)) ** 0.5) < 2e-3
+    assert float(net.conv1.weight.abs().max()) <= 1 / 512 ** 0.5 + 1e-6      # Conv2d default: U(+-1/sqrt(fan_in))
+    assert torch.equal(net.bn1.weight, torch.ones(128)) and torch.equal(net.bn1.running_var, torch.ones(128))
+
+
+def test_no_cpu_fallback():
+    net = networks.FCN(4, 2)
+    with pytest.raises(_lib.SimqError, match='no CPU fallback'):
+        net(torch.zeros(1, 4, 96, 96))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SimqError):
+            _lib.Ctx(0, 4, 2, 1)                                # simq_ctx_create fails loudly without a device
+
+
+def test_policy_surface():
+    class Cfg:
+        robot_config = [{'lifting_robot': 2}, {'pushing_robot': 2}]
+        num_input_channels, batch_size, final_exploration = 5, 8, 0.01
+        checkpoint_path = policy_path = None
+    pol = policies.DQNPolicy(Cfg(), train=True, device='cpu')
+    assert pol.num_robot_groups == 2 and [n.module.num_output_channels for n in pol.policy_nets] == [2, 1]
+    assert list(pol.policy_nets[0].state_dict())[0] == 'module.resnet18.conv1.weight'
+    s = synth.synth_states(1, 5, 0)[0]
+    t = pol.apply_transform(s)                                  # ToTensor on float32 HWC: transpose only, no /255
+    assert t.shape == (1, 5, 96, 96) and float(t.max()) == float(s.max())
+    tgt = pol.build_policy_nets()
+    tgt[0].load_state_dict(pol.policy_nets[0].state_dict())    # train.py:213-216
+    assert torch.equal(tgt[0].module.flat_params, pol.policy_nets[0].module.flat_params)
+
+
+def test_host_batch_compacts_next_states_like_the_reference():
+    batch = synth.synth_batch(8, 4, 2, 5, terminal_every=4)
+    hb = T.HostBatch(8, 4).fill(batch)
+    assert hb.Bn == 6 and hb.nonfinal.tolist() == [1, 1, 1, 0, 1, 1, 1, 0]
+    nf = [n for n in batch.next_state if n is not None]        # train.py:112
+    assert np.array_equal(hb.ns[:6].numpy(), np.stack(nf)) and np.array_equal(hb.s.numpy(), np.stack(batch.state))
+    assert hb.action.tolist() == list(batch.action)
+    with pytest.raises(ValueError):
+        T.HostBatch(4, 4).fill(batch)
+    sh = T.shard_batch(batch, 1, 2)
+    assert len(sh.state) == 4 and sh.action == batch.action[4:] and sh.next_state[3] is None
