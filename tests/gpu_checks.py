@@ -159,7 +159,7 @@ class Cfg:
         self.final_exploration, self.checkpoint_path, self.policy_path = 0.01, None, None
 
 
-def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False):
+def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False, resync=True):
     """nsteps updates on the GPU (fused simq_train_step, or the autograd path with a stock SGD exactly as
     the reference's train.py drives it) and in the oracle.  Returns a dict of error metrics."""
     pol, st = make_net(Cin, A, seed, max_batch=B, backend=backend)
@@ -190,6 +190,15 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
             gmap = {n: p.grad for n, p in pol.trainable()}
         out['loss'].append(info['loss']); out['td'].append(info['td_error'])
         out['loss_ref'].append(r['loss']); out['td_ref'].append(r['td_error'])
+        if resync and step + 1 < nsteps:
+            # teacher forcing: continue from the ORACLE's state (parameters, BN buffers, momentum), so that step k
+            # checks the k-th update itself (momentum rule, BN running statistics, counters) instead of the chaotic
+            # divergence of two trajectories (a Double-DQN arg-max flip on a B=8 batch moves the loss by several %)
+            out.setdefault('param_rel_l2_steps', []).append(
+                max(rel_l2(pol.state_dict()[n], o_pol[n]) for n in names))
+            pol.load_state_dict(o_pol)
+            for n, p in pol.trainable():
+                opt.state[p]['momentum_buffer'].copy_(o_mom[n])
         if step == 0:
             out['grad_rel_l2'] = {n: rel_l2(gmap[n], r['grads'][n]) for n in names}
             gn = float(torch.sqrt(sum((gmap[n].double() ** 2).sum() for n in names)))

@@ -114,16 +114,19 @@ def test_dqn_step_matches_oracle_and_golden(key, fused):
     r = G.train_step_check(C, A, B, seed, float(g[key + '_gamma']), te, nsteps, fused=fused)
     np.testing.assert_allclose(r['loss'][0], g[key + '_loss'][0], rtol=1e-3)
     np.testing.assert_allclose(r['td'][0], g[key + '_td'][0], rtol=1e-3)
-    # steps 2+ of the B=8 trajectory amplify step-1 rounding differences chaotically (arg-max / mask flips on a
-    # tiny batch: make_golden.py notes 1e-5 -> 30 % by step 5 even for the fp32 oracle), hence the loose bar there
-    np.testing.assert_allclose(r['loss'], r['loss_ref'], rtol=5e-2 if nsteps > 1 else 1e-3)
+    # multi-step: every step restarts from the oracle's state (teacher forcing, see gpu_checks.train_step_check):
+    # free-running B=8 trajectories diverge chaotically (a Double-DQN arg-max flip moves the loss by several %;
+    # make_golden.py notes 1e-5 -> 30 % by step 5 even for the fp32 oracle against the reference)
+    np.testing.assert_allclose(r['loss'], r['loss_ref'], rtol=1e-3)
+    np.testing.assert_allclose(r['td'], r['td_ref'], rtol=1e-3)
     _check_grads(r)
     worst = max(r['param_rel_l2'].items(), key=lambda kv: kv[1])
     assert worst[1] < (2e-3 if nsteps == 1 else 1e-2), f'parameter {worst[0]} rel-L2 {worst[1]:.3e}'
+    assert all(e < 1e-2 for e in r.get('param_rel_l2_steps', [])), r['param_rel_l2_steps']
     assert r['bn_err'] < 5e-3
     assert r['nbt'] == r['nbt_ref'] == list(g[key + '_nbt'])
     assert r['fc_untouched']
-    if r['mom_rel_l2'] is not None and nsteps == 1:
+    if r['mom_rel_l2'] is not None:
         assert max(v for n, v in r['mom_rel_l2'].items() if r['grad_ref_norm'][n] >= 1e-6 * r['grad_norm_ref']) < 5e-2
 
 
