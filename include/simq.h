@@ -37,7 +37,8 @@ typedef void* simq_stream;            /* cudaStream_t */
  * fp32 comparator for tests/debug (never the default). */
 enum { SIMQ_BACKEND_UMMA = 0, SIMQ_BACKEND_FMA = 1 };
 /* x layouts accepted by the stem */
-enum { SIMQ_X_NCHW = 0, SIMQ_X_NHWC = 1 };
+/* SIMQ_X_NHWC_PLUS1: [B,96,96,C+1] whose last channel is NOT a network input (train.py:145-146) */
+enum { SIMQ_X_NCHW = 0, SIMQ_X_NHWC = 1, SIMQ_X_NHWC_PLUS1 = 2 };
 
 const char* simq_last_error(void);
 int simq_version(void);
@@ -93,6 +94,18 @@ int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const flo
                     const float* reward, const uint8_t* nonfinal, int B, int Bn, float gamma, float lr,
                     float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
                     float* out2, simq_stream stream);
+
+/* Replaces nn.BCEWithLogitsLoss (mean) and its gradient, train.py:149-150.  q: n logits; target[i] at
+ * target + i*target_stride; out1[0] = loss; dq[n] = dL/dq. */
+int simq_bce_tail(simq_ctx*, const float* q, const float* target, int64_t target_stride, int64_t n, float* out1,
+                  float* dq, simq_stream stream);
+
+/* Replaces the whole of train.train_intention (train.py:143-158) for an FCN(C, 1) context: `state` is
+ * the replay states [B,96,96,C+1] NHWC; channels 0..C-1 are the input, channel C the target intention
+ * map.  Forward (train-mode BN), BCE-with-logits, backward, SGD (clip_norm<=0: none, as the reference). */
+int simq_intention_step(simq_ctx*, float* params, float* bn, int64_t* nbt, float* grads, float* momentum,
+                        const float* state, int B, float lr, float mom, float wd, float clip_norm, int first_step,
+                        int apply_update, float* out1, simq_stream stream);
 
 /* Replaces the greedy branch of DQNPolicy.step (policies.py:56-64): eval forward at batch B and
  * per-sample flat first-max argmax.  action_out: int64[B]; q (may be NULL) full Q-maps. */

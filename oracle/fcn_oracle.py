@@ -278,6 +278,32 @@ def dqn_step(policy, target, momentum: Optional[Dict[str, torch.Tensor]],
             'momentum': new_mom, 'q_sa': q_sa.detach(), 'target_y': y}
 
 
+def intention_step(net, momentum: Optional[Dict[str, torch.Tensor]], states_hwc: Sequence[np.ndarray], *,
+                   lr: float = 0.01, mom: float = 0.9, weight_decay: float = 1e-4, apply_update: bool = True):
+    """train.train_intention (train.py:143-158): ``net`` = state dict of FCN(C-1, 1) (mutated); ``states_hwc``:
+    (96,96,C) float32 arrays whose LAST channel is the ground-truth intention map.  BCEWithLogitsLoss
+    (mean), no gradient clipping, SGD(momentum 0.9, wd) as constructed at train.py:190."""
+    x = hwc_to_nchw([s[:, :, :-1] for s in states_hwc])                            # :145
+    target = hwc_to_nchw([s[:, :, -1:] for s in states_hwc])                       # :146
+    names = [n for n in net if net[n].is_floating_point() and net[n].dim() >= 1
+             and not n.endswith(('running_mean', 'running_var')) and not n.startswith('resnet18.fc.')]
+    leaves = {n: net[n].detach().clone().requires_grad_(True) for n in names}
+    work = OrderedDict(net)
+    work.update(leaves)
+    output = forward(work, x.to(net[names[0]].dtype), True)                         # :148
+    loss = F.binary_cross_entropy_with_logits(output, target.to(output.dtype))     # :149-150
+    grads_t = torch.autograd.grad(loss, [leaves[n] for n in names])                # :151-152
+    grads = OrderedDict((n, g.detach().clone()) for n, g in zip(names, grads_t))
+    new_mom = OrderedDict()
+    if apply_update:                                                               # :153
+        for n in names:
+            g = grads[n] + weight_decay * net[n]
+            buf = g.clone() if momentum is None else momentum[n] * mom + g
+            new_mom[n] = buf
+            net[n] = net[n] - lr * buf
+    return {'loss_intention': float(loss.item()), 'grads': grads, 'momentum': new_mom, 'output': output.detach()}
+
+
 # --------------------------------------------------------------------------------------
 # digests used by the golden fixtures (small, order-robust summaries of big tensors)
 # --------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libsimq.so')
 
 BACKEND_UMMA, BACKEND_FMA = 0, 1
-X_NCHW, X_NHWC = 0, 1
+X_NCHW, X_NHWC, X_NHWC_PLUS1 = 0, 1, 2
 N_BN = 22
 N_PARAM_TENSORS = 70
 
@@ -40,6 +40,9 @@ _PROTOS = {
     'simq_train_step': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, C.c_uint64, _p, _p, _p, _p, C.c_int, _p, _p, _p,
                                   C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_int, C.c_int, _p, _p]),
+    'simq_bce_tail': (C.c_int, [_c_ctx, _p, _p, C.c_int64, C.c_int64, _p, _p, _p]),
+    'simq_intention_step': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, _p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_int, _p, _p]),
     'simq_greedy_action': (C.c_int, [_c_ctx, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_uint64, _p]),
     'simq_launch_count': (C.c_int64, [_c_ctx]),
     'simq_profile': (C.c_int, [C.c_int, _p, _p, _p]),

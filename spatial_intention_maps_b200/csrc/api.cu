@@ -611,6 +611,31 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
     return 0;
 }
 
+extern "C" int simq_bce_tail(simq_ctx* c, const float* q, const float* target, int64_t target_stride, int64_t n, float* out1, float* dq,
+                             simq_stream stream) {
+    if (!c || !q || !target || !out1 || !dq || n < 1 || target_stride < 1) { simq_set_error("simq_bce_tail: bad argument"); return 1; }
+    return k_bce_tail(q, target, target_stride, n, out1, dq, c->dpartials, (cudaStream_t)stream);
+}
+
+extern "C" int simq_intention_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, float* grads, float* momentum,
+                                   const float* state, int B, float lr, float mom, float wd, float clip_norm, int first_step,
+                                   int apply_update, float* out1, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, state, B));
+    if (!grads || !momentum || !out1) { simq_set_error("simq_intention_step: NULL argument"); return 1; }
+    if (c->d.A != 1) { simq_set_error("simq_intention_step: the intention net has one output channel (A=%d)", c->d.A); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int err;
+    PackedSet* pw = get_packed(c, params, 0, s, &err);
+    if (err) return 1;
+    // train.py:145-148: inputs = all channels but the last, target = the last channel of the same state
+    TRY(run_forward(c, pw, params, bn, nbt, state, B, SIMQ_X_NHWC_PLUS1, 1, c->set[0], c->q_s, s));
+    TRY(k_bce_tail(c->q_s, state + c->d.C, c->d.C + 1, (long long)B * 9216, out1, c->dq, c->dpartials, s));     // :149-150
+    TRY(run_backward(c, pw, params, state, SIMQ_X_NHWC_PLUS1, c->dq, B, grads, s));                              // :151-152
+    if (apply_update)                                                                                           // :153
+        TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
+    return 0;
+}
+
 extern "C" int simq_greedy_action(simq_ctx* c, const float* params, const float* bn, const float* x, int B, int x_layout,
                                   int64_t* action_out, float* q, uint64_t params_version, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, x, B));

@@ -187,7 +187,9 @@ int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps,
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float stem_x(const float* __restrict__ x, int layout, int C, int n, int c, int y, int xx) {
     if (y < 0 || y >= 96 || xx < 0 || xx >= 96) return 0.f;
-    return layout == 0 ? x[(((size_t)n * C + c) * 96 + y) * 96 + xx] : x[(((size_t)n * 96 + y) * 96 + xx) * C + c];
+    if (layout == 0) return x[(((size_t)n * C + c) * 96 + y) * 96 + xx];
+    const int pix = layout == 2 ? C + 1 : C;      // layout 2: NHWC with one trailing non-input channel per pixel
+    return x[(((size_t)n * 96 + y) * 96 + xx) * pix + c];
 }
 
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int layout, int C,

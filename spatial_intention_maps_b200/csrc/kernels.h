@@ -26,6 +26,8 @@ int k_head_up2(const float* t, int B, int A, const float* b3, float* q, cudaStre
 int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const long long* action, const float* reward,
                const unsigned char* nonfinal, float gamma, int B, int Bn, int A, int double_dqn, float* per_sample,
                long long* best_action, float* out2, float* dq, cudaStream_t s);
+int k_bce_tail(const float* q, const float* target, long long tstride, long long n, float* out1, float* dq, double* partials,
+               cudaStream_t s);
 int k_argmax_rows(const float* q, int B, long long row_len, long long* idx_out, cudaStream_t s);
 int k_sgd_step(float* params, float* grads, float* momentum, long long n, float lr, float mom, float wd,
                float clip_norm, int first_step, double* partials, float* grad_norm_out, cudaStream_t s);

@@ -5,6 +5,7 @@
 #include "kernels.h"
 #include <math.h>
 
+#define SGD_BLOCKS 592
 #define BN_EPS 1e-5
 #define BN_MOM 0.1
 
@@ -424,9 +425,47 @@ int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const lon
 }
 
 // ------------------------------------------------------------------------------------------
+// BCEWithLogitsLoss (mean) + its gradient (train.py:149-150): q [n] logits, target strided
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bce_tail_kernel(const float* __restrict__ q, const float* __restrict__ target, long long tstride,
+                                                       long long n, float inv_n, float* __restrict__ dq, double* __restrict__ partials) {
+    __shared__ double sm[8];
+    double acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = q[i], t = target[i * tstride];
+        float e = expf(-fabsf(x));
+        acc += (double)(fmaxf(x, 0.f) - x * t + log1pf(e));
+        float sig = x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        dq[i] = (sig - t) * inv_n;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        partials[blockIdx.x] = t;
+    }
+}
+__global__ void bce_finalize_kernel(const double* __restrict__ partials, int nblk, double inv_n, float* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0;
+        for (int b = 0; b < nblk; ++b) t += partials[b];
+        out[0] = (float)(t * inv_n);
+    }
+}
+int k_bce_tail(const float* q, const float* target, long long tstride, long long n, float* out1, float* dq, double* partials,
+               cudaStream_t s) {
+    bce_tail_kernel<<<SGD_BLOCKS, 256, 0, s>>>(q, target, tstride, n, (float)(1.0 / (double)n), dq, partials);
+    SIMQ_LAUNCH_CHECK();
+    bce_finalize_kernel<<<1, 32, 0, s>>>(partials, SGD_BLOCKS, 1.0 / (double)n, out1);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // clip_grad_norm_ + SGD(momentum, weight decay)  (train.py:133-135, ctor :186)
 // ------------------------------------------------------------------------------------------
-#define SGD_BLOCKS 592
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ partials) {
     __shared__ double sm[8];
     double acc = 0;

@@ -183,3 +183,54 @@ def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_
     db.out2_host.copy_(db.out2, non_blocking=True)
     torch.cuda.current_stream().synchronize()       # the reference syncs here too: two .item() calls (train.py:138-139)
     return {'td_error': float(db.out2_host[1]), 'loss': float(db.out2_host[0])}
+
+
+def train_intention(intention_net, optimizer, batch, transform_fn):
+    """train.py:143-158 with the same arguments: one supervised update of the intention-prediction net
+    ``FCN(C-1, 1)`` -- input = all channels of ``batch.state`` but the last, target = the last channel,
+    ``BCEWithLogitsLoss`` (mean), backward, plain momentum-SGD (no clipping) -- as ONE call into the library
+    (``simq_intention_step``).  Returns ``{'loss_intention': float}``."""
+    net = _unwrap(intention_net)
+    B = len(batch.state)
+    Ct = net.num_input_channels + 1
+    dev = net.flat_params.device
+    cache = net.__dict__.setdefault('_intention_cache', {})
+    if cache.get('key') != (B, Ct, dev):
+        pin = torch.cuda.is_available()
+        cache.clear()
+        cache.update(key=(B, Ct, dev), host=torch.empty((B, 96, 96, Ct), dtype=torch.float32, pin_memory=pin),
+                     dev=torch.empty((B, 96, 96, Ct), dtype=torch.float32, device=dev),
+                     out=torch.zeros(1, dtype=torch.float32, device=dev),
+                     out_host=torch.zeros(1, dtype=torch.float32, pin_memory=pin))
+    h = cache['host'].numpy()
+    for i in range(B):
+        if batch.state[i].shape != (96, 96, Ct):
+            raise ValueError(f'state {i} has shape {batch.state[i].shape}, expected (96, 96, {Ct})')
+        h[i] = batch.state[i]
+    cache['dev'].copy_(cache['host'], non_blocking=True)
+    intention_step_device(net, optimizer, cache['dev'], B, cache['out'])
+    cache['out_host'].copy_(cache['out'], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return {'loss_intention': float(cache['out_host'][0])}
+
+
+def intention_step_device(net: FCN, optimizer, state_dev: torch.Tensor, B: int, out1: torch.Tensor):
+    g = optimizer.param_groups[0]
+    if g.get('nesterov') or g.get('dampening', 0) != 0:
+        raise _lib.SimqError('the fused step implements SGD(momentum, weight_decay) without nesterov/dampening (train.py:190)')
+    _momentum_views(net, optimizer)
+    ctx = net.ctx(B)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    first = 0 if net.momentum_initialized else 1
+    lr, mom, wd = float(g['lr']), float(g.get('momentum', 0.0)), float(g.get('weight_decay', 0.0))
+    grads = net.flat_grad()
+    L = _lib.lib()
+    _lib.check(L.simq_intention_step(ctx.handle, _lib.ptr(net.flat_params), _lib.ptr(net.flat_bn), _lib.ptr(net.flat_nbt),
+                                     _lib.ptr(grads), _lib.ptr(net.flat_momentum), _lib.ptr(state_dev), B, lr, mom, wd, 0.0, first,
+                                     1 if world == 1 else 0, _lib.ptr(out1), _lib.stream_ptr()), 'simq_intention_step')
+    if world > 1:
+        allreduce_mean_(grads, out1, world)
+        _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(net.flat_params), _lib.ptr(grads), _lib.ptr(net.flat_momentum),
+                                   lr, mom, wd, 0.0, first, None, _lib.stream_ptr()), 'simq_sgd_step')
+    net.momentum_initialized = True
+    net._manual_version += 1

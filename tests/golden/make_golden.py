@@ -186,7 +186,34 @@ def gen_policy():
     print('policy', acts)
 
 
+def gen_intention():
+    """train.train_intention (train.py:143-158) on the reference's DQNIntentionPolicy nets: 2 steps, B=8, C=5
+    (4 input channels + the ground-truth intention channel)."""
+    C, B, seed = 5, 8, 31
+    cfg = make_cfg(C, 'lifting_robot', B)
+    policy = policies.DQNIntentionPolicy(cfg, train=True)
+    net = policy.intention_nets[0]
+    load_ref(net, O.make_state(C - 1, 1, seed))
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)      # train.py:190
+    losses, grads = [], None
+    for step in range(2):
+        batch = ref_train.Transition(*synth.synth_batch(B, C, 2, seed + 1000 * step, terminal_every=None))
+        info = ref_train.train_intention(net, opt, batch, policy.apply_transform)
+        losses.append(info['loss_intention'])
+        if step == 0:
+            grads = {n[len('module.'):]: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+    after = ref_state(net)
+    names = O.trainable_names(C - 1, 1)
+    np.savez(os.path.join(HERE, 'intention.npz'), cfg=np.array([C, B, seed], dtype=np.int64), loss=np.array(losses),
+             grad_digest=np.stack([O.digest(grads[n]) for n in names]),
+             param_digest=np.stack([O.digest(after[n]) for n in names]),
+             nbt=np.array([int(after[n]) for n, _, k in O.state_spec(C - 1, 1) if k == 'nbt']))
+    print('intention', losses)
+
+
 if __name__ == '__main__':
-    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps']
+    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps', 'intention']
     for part in parts:
-        {'manifest': gen_manifest, 'forward': gen_forward, 'policy': gen_policy, 'steps': gen_steps}[part]()
+        {'manifest': gen_manifest, 'forward': gen_forward, 'policy': gen_policy, 'steps': gen_steps,
+         'intention': gen_intention}[part]()

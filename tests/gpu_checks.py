@@ -246,3 +246,36 @@ def reference_style_train(cfg, policy_net, target_net, optimizer, batch, discoun
     torch.nn.utils.clip_grad_norm_(policy_net.parameters(), cfg.grad_norm_clipping)
     optimizer.step()
     return {'td_error': td.mean().item(), 'loss': loss.item()}
+
+
+def intention_step_check(Ct, B, seed, nsteps=2, backend=_lib.BACKEND_UMMA):
+    """train_intention on the GPU (simq_intention_step) vs the oracle, teacher-forced between steps."""
+    net, st = make_net(Ct - 1, 1, seed, max_batch=B, backend=backend)
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)       # train.py:190
+    o_net, o_mom = O.clone_state(st), None
+    names = O.trainable_names(Ct - 1, 1)
+    out = {'loss': [], 'loss_ref': []}
+    for step in range(nsteps):
+        batch = synth.synth_batch(B, Ct, 2, seed + 1000 * step, terminal_every=None)
+        r = O.intention_step(o_net, o_mom, batch.state)
+        o_mom = r['momentum']
+        info = simq_train.train_intention(net, opt, batch, None)
+        out['loss'].append(info['loss_intention']); out['loss_ref'].append(r['loss_intention'])
+        if step == 0:
+            grads, po = net.flat_grad(), net._layout[2]
+            gmap = {n: grads[po[i]:po[i + 1]].view(p.shape) for i, (n, p) in enumerate(net.trainable())}
+            flat = lambda d: torch.cat([d[n].detach().double().cpu().reshape(-1) for n in names])
+            out['flat_grad_rel_l2'] = rel_l2(flat(gmap), flat(r['grads']))
+            out['grad_rel_l2'] = {n: rel_l2(gmap[n], r['grads'][n]) for n in names}
+            out['grad_ref_norm'] = {n: float(r['grads'][n].double().norm()) for n in names}
+            out['grad_norm_ref'] = float(flat(r['grads']).norm())
+        out.setdefault('param_rel_l2_steps', []).append(max(rel_l2(net.state_dict()[n], o_net[n]) for n in names))
+        if step + 1 < nsteps:
+            net.load_state_dict(o_net)
+            for n, p in net.trainable():
+                opt.state[p]['momentum_buffer'].copy_(o_mom[n])
+    sd = net.state_dict()
+    out['nbt'] = [int(sd[n]) for n, _, k in O.state_spec(Ct - 1, 1) if k == 'nbt']
+    out['nbt_ref'] = [int(o_net[n]) for n, _, k in O.state_spec(Ct - 1, 1) if k == 'nbt']
+    return out

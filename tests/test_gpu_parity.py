@@ -143,6 +143,22 @@ def test_gradients_against_float64_twin():
             assert e < max(1e-1, 10 * r['ref32_rel_l2_64'][n]), f'{n}: {e:.3e} (fp32 reference: {r["ref32_rel_l2_64"][n]:.3e})'
 
 
+def test_intention_step_matches_oracle_and_golden():
+    """train.train_intention (train.py:143-158): dense dL/dQ through the whole decoder backward; golden
+    losses from the reference's own train_intention (tests/golden/intention.npz)."""
+    g = np.load(os.path.join(GOLD, 'intention.npz'))
+    C, B, seed = [int(v) for v in g['cfg']]
+    r = G.intention_step_check(C, B, seed, nsteps=2)
+    np.testing.assert_allclose(r['loss'], g['loss'], rtol=1e-3)
+    np.testing.assert_allclose(r['loss'], r['loss_ref'], rtol=1e-3)
+    assert r['flat_grad_rel_l2'] < 3e-2, r['flat_grad_rel_l2']
+    for n, e in r['grad_rel_l2'].items():
+        if r['grad_ref_norm'][n] >= 1e-6 * r['grad_norm_ref']:
+            assert e < 1e-1, f'gradient {n} rel-L2 {e:.3e}'
+    assert all(e < 1e-2 for e in r['param_rel_l2_steps']), r['param_rel_l2_steps']
+    assert r['nbt'] == r['nbt_ref'] == list(g['nbt'])
+
+
 def test_policy_step_matches_golden():
     """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
     from oracle import fcn_oracle as O

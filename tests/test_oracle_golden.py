@@ -102,3 +102,24 @@ def test_greedy_action_matches_reference_policy_step():
         a, q = O.greedy_action(st, states[i])
         assert a == int(g['actions'][i])
         assert abs(float(q.max()) - float(g['qmax'][i])) <= 1e-5 * max(1.0, abs(float(g['qmax'][i])))
+
+
+def test_intention_step_matches_reference():
+    """train.train_intention (train.py:143-158) run by the reference itself (tests/golden/intention.npz)."""
+    g = np.load(os.path.join(G, 'intention.npz'))
+    C, B, seed = [int(v) for v in g['cfg']]
+    net = O.make_state(C - 1, 1, seed)
+    mom, losses, first = None, [], None
+    for step in range(2):
+        batch = synth.synth_batch(B, C, 2, seed + 1000 * step, terminal_every=None)
+        r = O.intention_step(net, mom, batch.state)
+        mom = r['momentum']
+        losses.append(r['loss_intention'])
+        first = first or r
+    np.testing.assert_allclose(losses, g['loss'], rtol=1e-5)
+    names = O.trainable_names(C - 1, 1)
+    gd = np.stack([O.digest(first['grads'][n]) for n in names])
+    np.testing.assert_allclose(gd[:, 2], g['grad_digest'][:, 2], rtol=2e-3, atol=1e-9)
+    pd = np.stack([O.digest(net[n]) for n in names])
+    np.testing.assert_allclose(pd[:, 2], g['param_digest'][:, 2], rtol=1e-5)
+    assert [int(net[n]) for n, _, k in O.state_spec(C - 1, 1) if k == 'nbt'] == list(g['nbt'])
