@@ -18,6 +18,8 @@
 #include "kernels.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -98,13 +100,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
@@ -127,10 +130,15 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 #define EPI_LD 36               // floats per staged row (32 + 4 pad: conflict-free float4 row writes and column reads)
 
+// BK = 64: 128-byte K rows, SWIZZLE_128B.  BK = 32: 64-byte K rows, SWIZZLE_64B -- used with BN = 256, where a
+// 64-wide stage would be 96 KB and only two would fit: four 48 KB stages hide the TMA latency better.
 template <int BN>
 struct ConvCfg {
-    static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // one plane of the A tile (16 KB)
-    static constexpr int W_BYTES = BN * UM_BK * 2;            // one plane of the W tile
+    static constexpr int BK = 64;
+    static constexpr int A_BYTES = UM_BM * BK * 2;            // one plane of the A tile
+    static constexpr int W_BYTES = BN * BK * 2;               // one plane of the W tile
+    static constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;    // SmemDescriptor layout_type
+    static constexpr uint32_t SBO = BK == 64 ? 1024u : 512u;  // 8 rows of BK*2 bytes
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4; // per epilogue warp: 32 rows x 32 columns fp32
     static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares
@@ -146,6 +154,106 @@ struct ConvCfg {
 // ------------------------------------------------------------------------------------------------
 // epilogue feature flags (compile-time: the epilogue is the bottleneck of the short-K layers)
 enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU = 32, EF_F32 = 64, EF_SPLIT = 128 };
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one 128 x BN tile (4 warps; warp `quad` owns TMEM lanes 32*quad..+31 = tile rows 32*quad..+31):
+// tcgen05.ld 32 columns -> smem staging -> [column sums] -> transforms -> coalesced row stores.
+// CLUSTER: the accumulator-free barrier lives in CTA 0 of the pair (remote arrive).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int FL, bool CLUSTER>
+__device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint32_t tmem_acc, uint32_t tempty, int m_t, int n0,
+                                              int rows, int N, float* __restrict__ out, const ConvEpilogue& ep, int quad, int lane) {
+    float* stg = staging + quad * 32 * EPI_LD;
+    float* cs = csum + quad * 2 * BN;
+    const int sr = lane >> 3, scol = (lane & 7) * 4;  // store phase: 4 rows per instruction, float4 per lane
+    const int mw = m_t * UM_BM + quad * 32;           // first row of this warp
+    const int m = mw + lane;
+    const bool valid = m < rows && !(ep.pitch25 && !p25_valid(m % IMG25));
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);      // bit r: row mw + r carries data
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+        if (c + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CLUSTER) {
+                    asm volatile(
+                        "{\n\t.reg .b32 ra;\n\t"
+                        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+                        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(tempty)
+                        : "memory");
+                } else {
+                    mbar_arrive(tempty);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 w4 = valid ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = w4;
+        }
+        __syncwarp();
+        if (FL & EF_STATS) {                    // lane = column: sums over this warp's 32 rows
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) { float x = stg[r * EPI_LD + lane]; s1 += x; s2 = fmaf(x, x, s2); }
+            cs[c + lane] = s1; cs[BN + c + lane] = s2;
+        }
+        const int n = n0 + c + scol;
+        float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FL & EF_AFFINE) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
+        const size_t o0 = (size_t)(mw + sr) * N + n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + sr;
+            if (mw + r >= rows) continue;
+            float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + scol);
+            const size_t o = o0 + (size_t)(i * 4) * N;
+            if ((vmask >> r) & 1u) {
+                if (FL & EF_AFFINE) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
+                if (FL & EF_PREV) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
+                if (FL & EF_RES) {
+                    uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
+                    const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
+                    x.x += bf2f(hb[0]) + bf2f(lb[0]); x.y += bf2f(hb[1]) + bf2f(lb[1]);
+                    x.z += bf2f(hb[2]) + bf2f(lb[2]); x.w += bf2f(hb[3]) + bf2f(lb[3]);
+                }
+                if (FL & EF_G) {
+                    float4 g = *reinterpret_cast<const float4*>(ep.add_g + o);
+                    uint2 mk = *reinterpret_cast<const uint2*>(ep.add_g_mask + o);
+                    const bf16* mb = reinterpret_cast<const bf16*>(&mk);
+                    if (bf2f(mb[0]) > 0.f) x.x += g.x;
+                    if (bf2f(mb[1]) > 0.f) x.y += g.y;
+                    if (bf2f(mb[2]) > 0.f) x.z += g.z;
+                    if (bf2f(mb[3]) > 0.f) x.w += g.w;
+                }
+                if (FL & EF_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            } else {
+                x = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (FL & EF_F32) *reinterpret_cast<float4*>(out + o) = x;
+            if (FL & EF_SPLIT) {
+                bf16 h[4], l[4];
+                split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
+                *reinterpret_cast<uint2*>(ep.out_split.hi + o) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(ep.out_split.lo + o) = *reinterpret_cast<const uint2*>(l);
+            }
+        }
+        __syncwarp();                           // staging is rewritten by the next chunk
+    }
+    if (FL & EF_STATS) {                        // combine the 4 warps in a fixed order -> one partial row per m_tile
+        epi_bar_sync();
+        const int t = threadIdx.x - 64;         // 0..127
+        for (int j = t; j < 2 * BN; j += 128) {
+            float tot = csum[j] + csum[2 * BN + j] + csum[4 * BN + j] + csum[6 * BN + j];
+            const int which = j / BN, col = j - which * BN;
+            ep.stats[((size_t)m_t * 2 + which) * N + n0 + col] = tot;
+        }
+        epi_bar_sync();
+    }
+}
 
 template <int BN, int FL>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -166,7 +274,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kchunks = K / UM_BK;
+    constexpr int BK = Cfg::BK;
+    const int kchunks = K / BK;
     const int iters = ntaps * kchunks;
     const int total_tiles = m_tiles * n_tiles;
 
@@ -196,10 +305,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
                     const int arow = m0 + off;
-                    tma_load_2d(sa, &mAhi, full_bar(s), kc * UM_BK, arow);
-                    tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * UM_BK, arow);
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * UM_BK, t * N + n0);
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * UM_BK, t * N + n0);
+                    tma_load_2d(sa, &mAhi, full_bar(s), kc * BK, arow);
+                    tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * BK, arow);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * BK, t * N + n0);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * BK, t * N + n0);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -218,11 +327,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     tc_fence_after();
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < UM_BK / 16; ++k) {
-                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
-                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
-                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
-                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
                         tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
                         tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
                         tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
@@ -236,91 +345,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
         }
     } else {
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
-        float* stg = staging + quad * 32 * EPI_LD;
-        float* cs = csum + quad * 2 * BN;
-        const int sr = lane >> 3, scol = (lane & 7) * 4;  // store phase: 4 rows per instruction, float4 per lane
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
-            const int mw = m_t * UM_BM + quad * 32;     // first row of this warp
-            const int m = mw + lane;
-            const bool valid = m < rows && !(ep.pitch25 && !p25_valid(m % IMG25));
-            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);      // bit r: row mw + r carries data
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (c + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 w4 = valid ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = w4;
-                }
-                __syncwarp();
-                if (FL & EF_STATS) {                    // lane = column: sums over this warp's 32 rows
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) { float x = stg[r * EPI_LD + lane]; s1 += x; s2 = fmaf(x, x, s2); }
-                    cs[c + lane] = s1; cs[BN + c + lane] = s2;
-                }
-                const int n = n0 + c + scol;
-                float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (FL & EF_AFFINE) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
-                const size_t o0 = (size_t)(mw + sr) * N + n;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + sr;
-                    if (mw + r >= rows) continue;
-                    float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + scol);
-                    const size_t o = o0 + (size_t)(i * 4) * N;
-                    if ((vmask >> r) & 1u) {
-                        if (FL & EF_AFFINE) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
-                        if (FL & EF_PREV) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
-                        if (FL & EF_RES) {
-                            uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
-                            const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
-                            x.x += bf2f(hb[0]) + bf2f(lb[0]); x.y += bf2f(hb[1]) + bf2f(lb[1]);
-                            x.z += bf2f(hb[2]) + bf2f(lb[2]); x.w += bf2f(hb[3]) + bf2f(lb[3]);
-                        }
-                        if (FL & EF_G) {
-                            float4 g = *reinterpret_cast<const float4*>(ep.add_g + o);
-                            uint2 mk = *reinterpret_cast<const uint2*>(ep.add_g_mask + o);
-                            const bf16* mb = reinterpret_cast<const bf16*>(&mk);
-                            if (bf2f(mb[0]) > 0.f) x.x += g.x;
-                            if (bf2f(mb[1]) > 0.f) x.y += g.y;
-                            if (bf2f(mb[2]) > 0.f) x.z += g.z;
-                            if (bf2f(mb[3]) > 0.f) x.w += g.w;
-                        }
-                        if (FL & EF_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    } else {
-                        x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (FL & EF_F32) *reinterpret_cast<float4*>(out + o) = x;
-                    if (FL & EF_SPLIT) {
-                        bf16 h[4], l[4];
-                        split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
-                        *reinterpret_cast<uint2*>(ep.out_split.hi + o) = *reinterpret_cast<const uint2*>(h);
-                        *reinterpret_cast<uint2*>(ep.out_split.lo + o) = *reinterpret_cast<const uint2*>(l);
-                    }
-                }
-                __syncwarp();                           // staging is rewritten by the next chunk
-            }
-            if (FL & EF_STATS) {                        // combine the 4 warps in a fixed order -> one partial row per m_tile
-                epi_bar_sync();
-                const int t = threadIdx.x - 64;         // 0..127
-                for (int j = t; j < 2 * BN; j += 128) {
-                    float tot = csum[j] + csum[2 * BN + j] + csum[4 * BN + j] + csum[6 * BN + j];
-                    const int which = j / BN, col = j - which * BN;
-                    ep.stats[((size_t)m_t * 2 + which) * N + n0 + col] = tot;
-                }
-                epi_bar_sync();
-            }
+            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N, out, ep,
+                                         quad, lane);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     }
@@ -329,6 +360,171 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for N % 256 == 0: a cluster of two CTAs on one TPC owns a 256 x 256 tile.
+// Each CTA stages its own 128 A rows and HALF of the W tile (128 of the 256 output channels); one
+// tcgen05.mma.cta_group::2 (M = 256, N = 256) issued by the leader CTA reads both halves, so per SM the
+// L2->smem traffic per MMA cycle is half that of the 128 x 128 single-CTA tile (64 KB per 1536 tensor cycles)
+// and the smem operand reads drop by a quarter.  Barriers: full[s] lives in the leader (both CTAs' TMA loads
+// complete_tx on it), empty[s] / tfull[a] exist in both CTAs and are signalled by multicast tcgen05.commit,
+// tempty[a] lives in the leader and collects the 8 epilogue warps of the pair.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+struct Conv2Cfg {
+    static constexpr int BN = 256;                            // pair tile: 256 rows x 256 columns
+    static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // this CTA's 128 A rows, one plane (16 KB)
+    static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of the W tile, one plane (16 KB)
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
+    static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
+    static constexpr int STAGES = 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+    static constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
+};
+
+template <int FL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
+conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
+                  int N, int ntaps, int m2_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
+    using Cfg = Conv2Cfg;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    float* staging = reinterpret_cast<float*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* csum = reinterpret_cast<float*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + Cfg::CSUM_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int kchunks = K / UM_BK;
+    const int iters = ntaps * kchunks;
+    const int total_tiles = m2_tiles * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mAhi); tma_prefetch_desc(&mAlo); tma_prefetch_desc(&mWhi); tma_prefetch_desc(&mWlo);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();             // barrier inits + TMEM allocation of both CTAs visible to the pair
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+                const int m2 = tile / n_tiles, n0 = (tile - m2 * n_tiles) * BN;
+                const int m0 = m2 * 256 + (int)rank * UM_BM;                 // this CTA's 128 rows
+                const int wn0 = n0 + (int)rank * (BN / 2);                   // this CTA's half of the output channels
+                for (int it = 0; it < iters; ++it) {
+                    const int t = it / kchunks, kc = it - t * kchunks;
+                    const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);   // bytes of BOTH CTAs land on the leader's barrier
+                    const uint32_t fb = mapa_rank0(full_bar(s));
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                    tma_load_2d_cg2(sa, &mAhi, fb, kc * UM_BK, m0 + off);
+                    tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 + off);
+                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES, &mWhi, fb, kc * UM_BK, t * N + wn0);
+                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc(256, BN, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t aph = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+                mbar_wait(tempty_bar(acc), aph ^ 1u);           // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
+                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
+                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
+                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
+                        tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                        tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                        tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                    }
+                    tc_commit_mc2(empty_bar(s));
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                }
+                tc_commit_mc2(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+            const int m2 = tile / n_tiles, n0 = (tile - m2 * n_tiles) * BN;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            epilogue_tile<BN, FL, true>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m2 * 2 + (int)rank, n0, rows, N,
+                                        out, ep, quad, lane);
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();             // nobody leaves while the peer may still touch its barriers / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -487,14 +683,14 @@ int umma_init() {
 }
 
 // bf16 [rows][cols] row-major, box [box_rows][64 cols], SWIZZLE_128B, zero fill out of bounds
-static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, int box_rows) {
+static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, int box_rows, int box_cols = 64) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { simq_set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%d box=%d)", (int)r, rows, cols, box_rows); return 1; }
     return 0;
 }
@@ -516,8 +712,8 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
     }
     if (A.rows >= (1LL << 31) - 256) { simq_set_error("k_conv_umma: too many rows"); return 1; }
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
-    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
-        make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
+    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM, Cfg::BK) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM, Cfg::BK) ||
+        make_map(&mWhi, W.t.hi, W.rows, W.cols, BN, Cfg::BK) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN, Cfg::BK))
         return 1;
     const int m_tiles = ceil_div(A.rows, UM_BM), n_tiles = N / BN;
     const int grid = m_tiles * n_tiles < g_num_sms ? m_tiles * n_tiles : g_num_sms;
@@ -530,8 +726,37 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
     return 0;
 }
 
+template <int FL>
+static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    using Cfg = Conv2Cfg;
+    static bool attr = false;
+    if (!attr) {
+        SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        SIMQ_CUDA(cudaGetDevice(&dev));
+        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap mAhi, mAlo, mWhi, mWlo;
+    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
+        make_map(&mWhi, W.t.hi, W.rows, W.cols, Cfg::BN / 2) || make_map(&mWlo, W.t.lo, W.rows, W.cols, Cfg::BN / 2))
+        return 1;
+    const int m2_tiles = ceil_div(A.rows, 256), n_tiles = N / Cfg::BN;
+    int clusters = g_num_sms / 2;
+    if (m2_tiles * n_tiles < clusters) clusters = m2_tiles * n_tiles;
+    const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
+    conv2_umma_kernel<FL><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m2_tiles,
+                                                                        n_tiles, out, ep);
+    prof_mark(PROF_CONV, false, 0, s);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 // the epilogue variants the network uses
-template <int BN>
+template <int BN, bool PAIR = false>
 static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     int fl = 0;
     if (ep.stats) fl |= EF_STATS;
@@ -543,7 +768,7 @@ static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     if (out) fl |= EF_F32;
     if (ep.out_split.hi) fl |= EF_SPLIT;
     switch (fl) {
-#define CASE(F) case (F): return launch_conv<BN, (F)>(A, W, N, ntaps, out, ep, s)
+#define CASE(F) case (F): return PAIR ? launch_conv2<(F)>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F)>(A, W, N, ntaps, out, ep, s)
         CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
         CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
         CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
@@ -568,6 +793,26 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         return 1;
     }
     if (N == 32) return dispatch_conv<32>(A, W, N, ntaps, out, ep, s);
+    // tile policy for N % 256 == 0: the CTA-pair kernel (256 x 256 per pair) runs ~12 % more tensor work per cycle
+    // than 128 x 128 single-CTA tiles but quantises worse on small problems; pick the cheaper estimate in units
+    // of one 128 x 128 tile time.  SIMQ_CONV_TILE = 128 | 256 | pair overrides (experiments).
+    static int policy = -1;
+    if (policy < 0) {
+        const char* e = getenv("SIMQ_CONV_TILE");
+        policy = !e ? 0 : !strcmp(e, "128") ? 1 : !strcmp(e, "256") ? 2 : !strcmp(e, "pair") ? 3 : 0;
+    }
+    if (N % 256 == 0 && policy != 1) {
+        if (!g_num_sms) {
+            int dev = 0;
+            SIMQ_CUDA(cudaGetDevice(&dev));
+            SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const long long t128 = (long long)ceil_div(A.rows, 128) * (N / 128), t256 = (long long)ceil_div(A.rows, 256) * (N / 256);
+        const double cost_single = (double)((t128 + g_num_sms - 1) / g_num_sms);
+        const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
+        if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, true>(A, W, N, ntaps, out, ep, s);
+        if (policy == 2) return dispatch_conv<256>(A, W, N, ntaps, out, ep, s);
+    }
     if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
     return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
 }
