@@ -159,7 +159,8 @@ class Cfg:
         self.final_exploration, self.checkpoint_path, self.policy_path = 0.01, None, None
 
 
-def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False, resync=True):
+def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False, resync=True,
+                     double_dqn=True):
     """nsteps updates on the GPU (fused simq_train_step, or the autograd path with a stock SGD exactly as
     the reference's train.py drives it) and in the oracle.  Returns a dict of error metrics."""
     pol, st = make_net(Cin, A, seed, max_batch=B, backend=backend)
@@ -169,6 +170,7 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
     pol.train()
     opt = torch.optim.SGD(pol.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)       # train.py:186
     cfg = Cfg(B, Cin)
+    cfg.use_double_dqn = double_dqn
     o_pol, o_tgt, o_mom = O.clone_state(st), O.clone_state(st), None
     out = {'loss': [], 'td': [], 'loss_ref': [], 'td_ref': []}
     names = O.trainable_names(Cin, A)
@@ -178,7 +180,7 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
             s_, a_, r_, ns_, m_ = batch_tensors(batch)
             r64 = O.dqn_step(O.clone_state(st, torch.float64), O.clone_state(st, torch.float64), None, s_.double(), a_,
                              r_.double(), ns_.double(), m_, discount=gamma, apply_update=False)
-        r = O.dqn_step(o_pol, o_tgt, o_mom, *batch_tensors(batch), discount=gamma)
+        r = O.dqn_step(o_pol, o_tgt, o_mom, *batch_tensors(batch), discount=gamma, double_dqn=double_dqn)
         o_mom = r['momentum']
         if fused:
             info = simq_train.train(cfg, pol, tgt, opt, batch, None, gamma)
@@ -236,8 +238,11 @@ def reference_style_train(cfg, policy_net, target_net, optimizer, batch, discoun
     nv = torch.zeros(cfg.batch_size, dtype=torch.float32, device=dev)
     with torch.no_grad():
         if ns.shape[0] > 0:
-            best = policy_net(ns).view(ns.size(0), -1).max(1)[1].view(ns.size(0), 1)
-            nv[mask] = target_net(ns).view(ns.size(0), -1).gather(1, best).view(-1)
+            if cfg.use_double_dqn:
+                best = policy_net(ns).view(ns.size(0), -1).max(1)[1].view(ns.size(0), 1)
+                nv[mask] = target_net(ns).view(ns.size(0), -1).gather(1, best).view(-1)
+            else:
+                nv[mask] = target_net(ns).view(ns.size(0), -1).max(1)[0]
     y = r + discount_factor * nv
     td = torch.abs(q - y).detach()
     loss = F.smooth_l1_loss(q, y)

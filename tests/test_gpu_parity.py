@@ -130,6 +130,22 @@ def test_dqn_step_matches_oracle_and_golden(key, fused):
         assert max(v for n, v in r['mom_rel_l2'].items() if r['grad_ref_norm'][n] >= 1e-6 * r['grad_norm_ref']) < 5e-2
 
 
+@pytest.mark.parametrize('case', ['all_terminal', 'batch1', 'plain_dqn', 'ragged_b37_c10_a1'])
+def test_dqn_step_edge_cases(case):
+    """Edges of train.py:108-141: every transition terminal (empty next-state batch: train.py:112 would cat an
+    empty list, the target term vanishes), a single-sample batch (BN statistics over one image), the
+    non-double branch (train.py:124), and a ragged batch (B=37: M = 23125 rows is not a tile multiple) with
+    the widest input (C=10) and one output channel."""
+    C, A, B, te, dd = {'all_terminal': (4, 2, 4, 1, True), 'batch1': (4, 2, 1, 2, True), 'plain_dqn': (5, 2, 8, 4, False),
+                       'ragged_b37_c10_a1': (10, 1, 37, 5, True)}[case]
+    for fused in (True, False):
+        r = G.train_step_check(C, A, B, 40 + B, 0.85, te, 1, fused=fused, double_dqn=dd)
+        np.testing.assert_allclose(r['loss'], r['loss_ref'], rtol=1e-3)
+        np.testing.assert_allclose(r['td'], r['td_ref'], rtol=1e-3)
+        assert r['flat_grad_rel_l2'] < (3e-2 if B > 1 else 1e-1), r['flat_grad_rel_l2']
+        assert r['nbt'] == r['nbt_ref'] and r['fc_untouched'] and r['bn_err'] < 5e-3
+
+
 def test_gradients_against_float64_twin():
     """c1: our gradient error against the float64 twin of the reference must be of the order of the
     fp32 reference's own error against it."""
