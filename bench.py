@@ -231,6 +231,13 @@ def run_simq(args):
 
     if rank == 0:
         sustained, burst, hbm, how = peaks()
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj['dram_bytes']
+            traffic_note = (f"{tj['launch']}: {tj['dram_bytes'] / 1e6:.0f} MB DRAM vs {tj['algorithmic_bytes'] / 1e6:.0f} MB algorithmic, "
+                            f"tensor pipe {tj['tensor_pipe_active_pct']:.0f} % active ({tj['source']})")
         conv_tf = (pf[0] / (pm[0] * 1e-3)) / 1e12 if pm[0] > 0 else 0.0
         wgrad_tf = (pf[1] / (pm[1] * 1e-3)) / 1e12 if pm[1] > 0 else 0.0
         per_step = ms_dev / args.steps
@@ -247,8 +254,8 @@ def run_simq(args):
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': hb.h2d_bytes(), 'd2h_bytes_per_step': 8,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (tcgen05 3x3/1x1 conv + dgrad)', 'achieved': conv_tf, 'peak': sustained / 1.0,
-                         'unit': 'TFLOP/s', 'frac': conv_tf / sustained, 'traffic': None, 'peak_source': f'{how} bf16 sustained',
+            'roofline': {'bound': 'tensor', 'kernel': 'conv2_umma_kernel / conv_umma_kernel (tcgen05 conv + dgrad, all launches of the step)', 'achieved': conv_tf, 'peak': sustained / 1.0,
+                         'unit': 'TFLOP/s', 'frac': conv_tf / sustained, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': f'{how} bf16 sustained',
                          'launches': int(pl[0]), 'ms_per_step_in_kernel': pm[0] / args.steps,
                          'share_of_step': (pm[0] / args.steps) / per_step,
                          'note': 'algorithmic FLOPs (2*valid_pixels*N*K*taps); the kernel issues 3 bf16 MMAs per product over 625/576 padded rows, '

@@ -447,14 +447,19 @@ extern "C" int simq_fcn_forward(simq_ctx* c, const float* params, float* bn, int
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// nparts > 0: the dgrad epilogue that produced G already left `nparts` rows of (sum dz, sum dz*xhat) in c->partials
 static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, long long rows, double count, int mask_mode,
                        const bf16* mask_hi, const float* raw, const float* params, float* grads, int pitch25, Split dy,
-                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, cudaStream_t s) {
+                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, cudaStream_t s) {
     const NetDesc& d = c->d;
-    TRY(k_bn_bwd_reduce(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
-                        bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr,
-                        bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr, c->partials, s));
-    TRY(k_reduce_partials(c->partials, STAT_BLOCKS, 3 * b.ch, c->sums, 1.0f, s));
+    if (nparts > 0) {
+        TRY(k_reduce_partials(c->partials, nparts, 2 * b.ch, c->sums, 1.0f, s));
+    } else {
+        TRY(k_bn_bwd_reduce(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
+                            bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr,
+                            bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr, c->partials, s));
+        TRY(k_reduce_partials(c->partials, STAT_BLOCKS, 3 * b.ch, c->sums, 1.0f, s));
+    }
     TRY(k_bn_bwd_apply(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
                        bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), params + d.poff[b.gamma], c->sums, count, pitch25, dy,
                        dy_f32, rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr, bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr,
@@ -497,11 +502,29 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     float* G = c->G[0];
     float* Gn = c->G[1];
     TRY(k_up1_adj(c->du1, B, G, s));
-    TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr, none, s));
+    TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr, none, 0, s));
     TRY(bias_grad(c, c->dyA, R25, 128, grads + d.poff[d.h1_bias], s));
     TRY(wgrad_any(c, be, c->dyA, S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w], s));
     ConvEpilogue ep25 = conv_ep(1);
-    TRY(conv_any(c, be, c->dyA, R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, ep25, s));
+    // With the tcgen05 back-end the dgrad launch that PRODUCES a gradient also reduces the BatchNorm-backward sums of
+    // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
+    // with a downsample branch need a third sum and keep the separate reduction.
+    const bool fuse = be == SIMQ_BACKEND_UMMA;
+    const int nparts_fused = umma_conv_m_tiles(R25);
+    // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
+    auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
+        if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
+            e.stats = c->partials; e.bn_raw = raw; e.bn_mask = mask;
+            e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
+        }
+        return e;
+    };
+    int g_parts = 0;                 // partial rows already available for the BN consuming G
+    {
+        ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
+        TRY(conv_any(c, be, c->dyA, R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, s));
+        g_parts = e.bn_raw ? nparts_fused : 0;
+    }
     { float* t = G; G = Gn; Gn = t; }
     // ---- residual stages, last to first ----
     for (int b = 7; b >= 0; --b) {
@@ -511,20 +534,32 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
         // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
         TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, c->dyA, nullptr, P.has_ds ? &P.bds : nullptr,
-                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, s));
+                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, s));
         TRY(wgrad_any(c, be, c->dyA, Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w], s));
-        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, ep25, s));
+        ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
+        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, s));
         if (P.has_ds) TRY(wgrad_any(c, be, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w], s));
         // b1 = relu(bn1(raw1))
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr,
-                        none, s));
+                        none, em.bn_raw ? nparts_fused : 0, s));
         TRY(wgrad_any(c, be, c->dyA, in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w], s));
+        // gradient w.r.t. the block input = the previous block's output (or the stem's pooled output for b == 0)
+        const bool consumer_fusable = b > 0 && !d.blk[b - 1].has_ds;
         ConvEpilogue ep = ep25;
         if (!P.has_ds) { ep.add_g = G; ep.add_g_mask = Ab.out.hi; }
+        g_parts = 0;
+        if (consumer_fusable && !P.has_ds) {
+            ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
+            g_parts = ep.bn_raw ? nparts_fused : 0;
+        }
         TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, s));
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
+            if (consumer_fusable) {
+                epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
+                g_parts = epd.bn_raw ? nparts_fused : 0;
+            }
             TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, s));
         }
         { float* t = G; G = Gn; Gn = t; }
@@ -533,11 +568,11 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     const int sb = d.stem_bn.idx;
     TRY(k_pool_bwd(G, S.raw0, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
     if (be == SIMQ_BACKEND_UMMA) {
-        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, s));
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, 0, s));
         TRY(wgrad_any(c, be, c->dy0s, S.acol, R48, 64, stem_kp(d.C), 1, c->stem_tmp, s));
         TRY(k_strip_stem(c->stem_tmp, d.C, stem_kp(d.C), grads + d.poff[d.stem.w], s));
     } else {
-        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, s));
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, 0, s));
         TRY(k_stem_wgrad(x, x_layout, B, d.C, c->dy0, c->stem_partials, grads + d.poff[d.stem.w], s));
     }
     return 0;

@@ -153,7 +153,7 @@ struct ConvCfg {
 // double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // ------------------------------------------------------------------------------------------------
 // epilogue feature flags (compile-time: the epilogue is the bottleneck of the short-K layers)
-enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU = 32, EF_F32 = 64, EF_SPLIT = 128 };
+enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU = 32, EF_F32 = 64, EF_SPLIT = 128, EF_BNBWD = 256 };
 
 // ------------------------------------------------------------------------------------------------
 // epilogue of one 128 x BN tile (4 warps; warp `quad` owns TMEM lanes 32*quad..+31 = tile rows 32*quad..+31):
@@ -234,6 +234,7 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
                 x = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (FL & EF_F32) *reinterpret_cast<float4*>(out + o) = x;
+            if (FL & EF_BNBWD) *reinterpret_cast<float4*>(stg + r * EPI_LD + scol) = x;     // final gradient back to staging
             if (FL & EF_SPLIT) {
                 bf16 h[4], l[4];
                 split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
@@ -242,8 +243,25 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
             }
         }
         __syncwarp();                           // staging is rewritten by the next chunk
+        if (FL & EF_BNBWD) {                    // lane = column: BatchNorm-backward sums of this warp's 32 rows
+            const int col = n0 + c + lane;
+            const float mu = ep.bn_mean[col], is = ep.bn_invstd[col];
+            float s1 = 0.f, s2 = 0.f;
+            const int rmax = rows - mw < 32 ? rows - mw : 32;
+#pragma unroll 8
+            for (int r = 0; r < rmax; ++r) {
+                const size_t o = (size_t)(mw + r) * N + col;
+                const float g = stg[r * EPI_LD + lane];
+                const float xr = ep.bn_raw[o];
+                const float dz = bf2f(ep.bn_mask[o]) > 0.f ? g : 0.f;
+                s1 += dz;
+                s2 = fmaf(dz, (xr - mu) * is, s2);
+            }
+            cs[c + lane] = s1; cs[BN + c + lane] = s2;
+            __syncwarp();
+        }
     }
-    if (FL & EF_STATS) {                        // combine the 4 warps in a fixed order -> one partial row per m_tile
+    if (FL & (EF_STATS | EF_BNBWD)) {           // combine the 4 warps in a fixed order -> one partial row per m_tile
         epi_bar_sync();
         const int t = threadIdx.x - 64;         // 0..127
         for (int j = t; j < 2 * BN; j += 128) {
@@ -876,7 +894,7 @@ static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int nta
 template <int BN, bool PAIR = false>
 static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     int fl = 0;
-    if (ep.stats) fl |= EF_STATS;
+    if (ep.stats && !ep.bn_raw) fl |= EF_STATS;
     if (ep.scale) fl |= EF_AFFINE;
     if (ep.add_prev) fl |= EF_PREV;
     if (ep.res.hi) fl |= EF_RES;
@@ -884,12 +902,16 @@ static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     if (ep.relu) fl |= EF_RELU;
     if (out) fl |= EF_F32;
     if (ep.out_split.hi) fl |= EF_SPLIT;
+    if (ep.bn_raw) fl |= EF_BNBWD;
     switch (fl) {
 #define CASE(F) case (F): return PAIR ? launch_conv2<(F)>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F)>(A, W, N, ntaps, out, ep, s)
         CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
         CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
         CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
         CASE(EF_F32 | EF_G);                                        // dgrad + masked identity gradient
+        CASE(EF_F32 | EF_BNBWD);                                    // dgrad + BN-backward sums of the consumer BN
+        CASE(EF_F32 | EF_PREV | EF_BNBWD);
+        CASE(EF_F32 | EF_G | EF_BNBWD);
         CASE(EF_F32 | EF_AFFINE);                                   // eval downsample: BN'd identity
         CASE(EF_SPLIT | EF_AFFINE | EF_RELU);                       // eval conv1 -> BN -> ReLU
         CASE(EF_SPLIT | EF_AFFINE | EF_RELU | EF_RES);              // eval conv2 -> BN -> + identity -> ReLU

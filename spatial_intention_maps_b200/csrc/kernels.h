@@ -81,11 +81,15 @@ struct ConvEpilogue {
     int relu;
     Split out_split;          // write v as split bf16 (out may then be NULL)
     float* stats;             // [m_tiles][2][N] per-tile column sums / sums of squares of the raw accumulators
+    // BatchNorm-backward statistics of the gradient this launch produces (dgrad): with dz = out * [bn_mask > 0],
+    // stats rows become (sum dz, sum dz * (bn_raw - mean) * invstd) -- saves the separate reduction pass
+    const float* bn_raw; const bf16* bn_mask; const float* bn_mean; const float* bn_invstd;
 };
 static inline ConvEpilogue conv_ep(int pitch25) {
     ConvEpilogue e;
     e.pitch25 = pitch25; e.add_prev = nullptr; e.add_g = nullptr; e.add_g_mask = nullptr; e.scale = nullptr; e.shift = nullptr;
     e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
+    e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr;
     return e;
 }
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
