@@ -95,6 +95,11 @@ int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const flo
                     float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
                     float* out2, simq_stream stream);
 
+/* Replay-batch assembly on the device (replaces the per-sample transform + torch.cat + H2D of
+ * train.py:109-112 when the replay buffer is device-resident): dst[j][:] = src[idx[j]][:], rows of
+ * row_floats fp32 (multiple of 4), idx on the device. */
+int simq_gather_rows(const float* src, const int64_t* idx, int n, int64_t row_floats, float* dst, simq_stream stream);
+
 /* Replaces nn.BCEWithLogitsLoss (mean) and its gradient, train.py:149-150.  q: n logits; target[i] at
  * target + i*target_stride; out1[0] = loss; dq[n] = dL/dq. */
 int simq_bce_tail(simq_ctx*, const float* q, const float* target, int64_t target_stride, int64_t n, float* out1,

@@ -293,7 +293,7 @@ static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows
         UmmaTensor y{dY, rows, Cout}, x{X, rows, Cin};
         return k_wgrad_umma(y, x, ntaps, dW, c->wscratch, s);
     }
-    return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, s);
+    return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, c->wscratch, s);
 }
 
 static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version, cudaStream_t s, int* err) {
@@ -644,6 +644,11 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
     if (apply_update)
         TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
     return 0;
+}
+
+extern "C" int simq_gather_rows(const float* src, const int64_t* idx, int n, int64_t row_floats, float* dst, simq_stream stream) {
+    if (n < 0 || (n > 0 && (!src || !idx || !dst)) || row_floats < 4) { simq_set_error("simq_gather_rows: bad argument"); return 1; }
+    return k_gather_rows(src, (const long long*)idx, n, row_floats, dst, (cudaStream_t)stream);
 }
 
 extern "C" int simq_bce_tail(simq_ctx* c, const float* q, const float* target, int64_t target_stride, int64_t n, float* out1, float* dq,

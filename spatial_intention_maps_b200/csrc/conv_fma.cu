@@ -103,12 +103,12 @@ int k_conv_fma(Split A, long long rows, int K, Split W, int N, int ntaps, float*
 // dW[co][ci][t] = sum_p dY[p][co] * X[p + off_t][ci]       (OIHW output, atomics across row splits)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wgrad_fma_kernel(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps,
-                                                        int nsplit, float* __restrict__ dW) {
+                                                        int nsplit, float* __restrict__ partial) {
     __shared__ float Ys[FK][FB + 4];
     __shared__ float Xs[FK][FB + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int co0 = blockIdx.x * FB, ci0 = blockIdx.y * FB;
-    const int t = blockIdx.z / nsplit, sp = blockIdx.z % nsplit;
+    const int t = blockIdx.z % ntaps, sp = blockIdx.z / ntaps;
     const int off = tap_offset(t, ntaps);
     long long chunk = ((rows + nsplit - 1) / nsplit + FK - 1) / FK * FK;
     long long p_begin = (long long)sp * chunk, p_end = p_begin + chunk;
@@ -163,22 +163,23 @@ __global__ void __launch_bounds__(256) wgrad_fma_kernel(Split dY, Split X, long 
         for (int j = 0; j < 4; ++j) {
             int ci = ci0 + tx * 4 + j;
             if (ci >= Cin) continue;
-            atomicAdd(dW + ((size_t)co * Cin + ci) * ntaps + t, acc[i][j]);
+            partial[((size_t)blockIdx.z * Cout + co) * Cin + ci] = acc[i][j];     // z = sp*ntaps + t
         }
     }
 }
 
-int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW, cudaStream_t s) {
-    SIMQ_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Cout * Cin * ntaps, s));
+int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW, float* scratch, cudaStream_t s) {
     int base = ceil_div(Cout, FB) * ceil_div(Cin, FB) * ntaps;
     int nsplit = (1184 + base - 1) / base;
     long long max_split = rows / 512; if (max_split < 1) max_split = 1;
     if (nsplit > max_split) nsplit = (int)max_split;
     if (nsplit < 1) nsplit = 1;
     dim3 grid(ceil_div(Cout, FB), ceil_div(Cin, FB), ntaps * nsplit);
-    wgrad_fma_kernel<<<grid, 256, 0, s>>>(dY, X, rows, Cout, Cin, ntaps, nsplit, dW);
+    while (nsplit > 1 && (size_t)nsplit * ntaps * Cout * Cin > umma_wgrad_scratch_floats()) --nsplit;
+    grid.z = ntaps * nsplit;
+    wgrad_fma_kernel<<<grid, 256, 0, s>>>(dY, X, rows, Cout, Cin, ntaps, nsplit, scratch);
     SIMQ_LAUNCH_CHECK();
-    return 0;
+    return k_wgrad_reduce(scratch, Cout, Cin, ntaps, nsplit, dW, s);      // fixed summation order: deterministic
 }
 
 // ------------------------------------------------------------------------------------------

@@ -802,6 +802,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     dW[(size_t)r * ntaps + t] = acc;
 }
 
+int k_wgrad_reduce(const float* partial, int Cout, int Cin, int ntaps, int nsplit, float* dW, cudaStream_t s) {
+    long long n = (long long)Cout * Cin * ntaps;
+    wgrad_reduce_kernel<<<ceil_div(n, 256), 256, 0, s>>>(partial, Cout, Cin, ntaps, nsplit, dW);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const lon
                long long* best_action, float* out2, float* dq, cudaStream_t s);
 int k_bce_tail(const float* q, const float* target, long long tstride, long long n, float* out1, float* dq, double* partials,
                cudaStream_t s);
+int k_gather_rows(const float* src, const long long* idx, int n, long long row_floats, float* dst, cudaStream_t s);
 int k_argmax_rows(const float* q, int B, long long row_len, long long* idx_out, cudaStream_t s);
 int k_sgd_step(float* params, float* grads, float* momentum, long long n, float lr, float mom, float wd,
                float clip_norm, int first_step, double* partials, float* grad_norm_out, cudaStream_t s);
@@ -95,7 +96,8 @@ static inline ConvEpilogue conv_ep(int pitch25) {
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
 int k_conv_fma(Split A, long long rows, int K, Split W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
 // dW[co][ci][tap] (OIHW) = sum_p dY[p][co] * X[p+off_tap][ci]   (zero-inits dW itself)
-int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW, cudaStream_t s);
+int k_wgrad_fma(Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW, float* scratch, cudaStream_t s);
+int k_wgrad_reduce(const float* partial, int Cout, int Cin, int ntaps, int nsplit, float* dW, cudaStream_t s);
 int k_stem_conv(const float* x, int x_layout, int B, int C, const float* w, float* raw0, cudaStream_t s);
 int k_stem_wgrad(const float* x, int x_layout, int B, int C, const float* dy0, float* partials, float* dW,
                  cudaStream_t s);

@@ -994,6 +994,23 @@ int k_head2_scatter(const float* sums, int A, float* dgamma2, float* dbeta2, flo
     return 0;
 }
 
+// dst[j][:] = src[idx[j]][:]  (rows of row_floats fp32, multiple of 4): replay-batch assembly on the device
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ src, const long long* __restrict__ idx,
+                                                          long long row_vec, float4* __restrict__ dst) {
+    const long long j = blockIdx.y;
+    const float4* s = src + idx[j] * row_vec;
+    float4* d = dst + j * row_vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_vec; i += (long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+int k_gather_rows(const float* src, const long long* idx, int n, long long row_floats, float* dst, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (row_floats % 4) { simq_set_error("k_gather_rows: row length %lld not a multiple of 4", row_floats); return 1; }
+    dim3 grid(16, n);
+    gather_rows_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), idx, row_floats / 4, reinterpret_cast<float4*>(dst));
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // debug / test import-export between dense NCHW f32 and the internal layouts
 // ------------------------------------------------------------------------------------------

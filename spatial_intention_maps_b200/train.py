@@ -176,8 +176,19 @@ def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_
         cache.clear()
         cache.update(key=(B, C, dev), host=HostBatch(B, C), dev=DeviceBatch(B, C, dev))
     hb, db = cache['host'], cache['dev']
-    hb.fill(batch)
-    db.upload(hb)
+    from .replay import DeviceSample
+    if isinstance(batch, DeviceSample):          # device-resident replay buffer: gather, no host staging of the states
+        if len(batch) != B:
+            raise ValueError(f'batch has {len(batch)} transitions, expected {B}')
+        action, reward, nonfinal, Bn = batch.buffer.gather(batch, db.s, db.ns)
+        hb.action.numpy()[:] = action; hb.reward.numpy()[:] = reward; hb.nonfinal.numpy()[:] = nonfinal
+        db.action.copy_(hb.action, non_blocking=True)
+        db.reward.copy_(hb.reward, non_blocking=True)
+        db.nonfinal.copy_(hb.nonfinal, non_blocking=True)
+        db.Bn = hb.Bn = Bn
+    else:
+        hb.fill(batch)
+        db.upload(hb)
     train_step_device(policy, target, optimizer, db, B, discount_factor, getattr(cfg, 'grad_norm_clipping', None),
                       bool(getattr(cfg, 'use_double_dqn', True)))
     db.out2_host.copy_(db.out2, non_blocking=True)

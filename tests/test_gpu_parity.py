@@ -175,6 +175,33 @@ def test_intention_step_matches_oracle_and_golden():
     assert r['nbt'] == r['nbt_ref'] == list(g['nbt'])
 
 
+def test_device_replay_buffer_feeds_the_same_update():
+    """train.train on a DeviceSample (device gather, simq_gather_rows) == train.train on the equivalent host
+    Transition batch, bit for bit."""
+    import random
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    from spatial_intention_maps_b200.replay import ReplayBuffer
+    tr = synth.synth_batch(24, 5, 2, 9, terminal_every=5)
+    buf = ReplayBuffer(20)                                      # wraps: 24 pushes into 20 slots
+    for i in range(24):
+        buf.push(tr.state[i], tr.action[i], tr.reward[i], tr.next_state[i])
+    random.seed(3)
+    sample = buf.sample(8)
+    host_batch = sample.to_transition()
+    losses = []
+    for batch in (sample, host_batch):
+        net, st = G.make_net(5, 2, 17, max_batch=8)
+        tgt = networks.FCN(5, 2, max_batch=8)
+        tgt.load_state_dict(st)
+        tgt = tgt.to(G.DEV).eval()
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        info = T.train(G.Cfg(8, 5), net, tgt, opt, batch, None, 0.85)
+        losses.append((info['loss'], info['td_error'], net.flat_params.clone()))
+    assert losses[0][0] == losses[1][0] and losses[0][1] == losses[1][1]
+    assert torch.equal(losses[0][2], losses[1][2])
+
+
 def test_policy_step_matches_golden():
     """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
     from oracle import fcn_oracle as O

@@ -118,3 +118,53 @@ def test_host_batch_compacts_next_states_like_the_reference():
         T.HostBatch(4, 4).fill(batch)
     sh = T.shard_batch(batch, 1, 2)
     assert len(sh.state) == 4 and sh.action == batch.action[4:] and sh.next_state[3] is None
+
+
+class _RefReplayBuffer:
+    """The reference's ReplayBuffer, train.py:28-45, restated for the comparison below."""
+
+    def __init__(self, capacity):
+        self.capacity, self.buffer, self.position = capacity, [], 0
+
+    def push(self, *args):
+        if len(self.buffer) < self.capacity:
+            self.buffer.append(None)
+        self.buffer[self.position] = T.Transition(*args)
+        self.position = (self.position + 1) % self.capacity
+
+    def sample(self, batch_size):
+        import random
+        return T.Transition(*zip(*random.sample(self.buffer, batch_size)))
+
+    def __len__(self):
+        return len(self.buffer)
+
+
+def test_replay_buffer_matches_reference_semantics():
+    import pickle
+    import random
+    from spatial_intention_maps_b200.replay import ReplayBuffer
+    ours, ref = ReplayBuffer(6, device='cpu'), _RefReplayBuffer(6)
+    tr = synth.synth_batch(10, 4, 2, 3, terminal_every=3)
+    for i in range(10):                                         # wraps around: capacity 6
+        for b in (ours, ref):
+            b.push(tr.state[i], tr.action[i], tr.reward[i], tr.next_state[i])
+        assert len(ours) == len(ref)
+    for seed in (0, 1):
+        random.seed(seed); a = ours.sample(4)
+        random.seed(seed); b = ref.sample(4)
+        at = a.to_transition()
+        assert at.action == b.action and np.allclose(at.reward, b.reward)
+        for x, y in zip(at.state, b.state):
+            assert np.array_equal(x, y)
+        for x, y in zip(at.next_state, b.next_state):
+            assert (x is None and y is None) or np.array_equal(x, y)
+        out_s, out_ns = torch.zeros(4, 96, 96, 4), torch.zeros(4, 96, 96, 4)
+        action, reward, nf, Bn = ours.gather(a, out_s, out_ns)
+        assert Bn == sum(n is not None for n in b.next_state) and list(action) == list(b.action)
+        assert np.array_equal(out_ns[:Bn].numpy(), np.stack([n for n in b.next_state if n is not None]))
+    clone = pickle.loads(pickle.dumps(ours))                    # train.py:331 checkpoints the buffers with torch.save
+    assert len(clone) == 6 and clone.position == ours.position
+    random.seed(5); x = clone.sample(3).to_transition()
+    random.seed(5); y = ours.sample(3).to_transition()
+    assert x.action == y.action and all(np.array_equal(p, q) for p, q in zip(x.state, y.state))
