@@ -96,4 +96,13 @@ void simq_set_error(const char* fmt, ...);
         }                                                                                        \
     } while (0)
 
+// true the first time a call site runs on the current device (bit mask per device)
+static inline bool first_use_on_device(unsigned long long& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((mask >> dev) & 1ull) return false;
+    mask |= 1ull << dev;
+    return true;
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -308,11 +308,8 @@ __global__ void __launch_bounds__(256, 1) stem_wgrad_kernel(const float* __restr
 int k_stem_wgrad(const float* x, int x_layout, int B, int C, const float* dy0, float* partials, float* dW,
                  cudaStream_t s) {
     size_t smem = sizeof(float) * (16 * 64 + 16 * 512);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SIMQ_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(attr_set)) SIMQ_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stem_wgrad_kernel<<<SW_BLOCKS, 256, smem, s>>>(x, x_layout, B, C, dy0, partials);
     SIMQ_LAUNCH_CHECK();
     return k_reduce_partials(partials, SW_BLOCKS, 64 * C * 49, dW, 1.0f, s);

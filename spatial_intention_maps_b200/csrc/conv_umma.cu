@@ -842,11 +842,8 @@ static int g_num_sms = 0;
 template <int BN, int FL>
 static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     using Cfg = ConvCfg<BN>;
-    static bool attr = false;
-    if (!attr) {
-        SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));
@@ -871,11 +868,8 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
 template <int FL>
 static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     using Cfg = Conv2Cfg;
-    static bool attr = false;
-    if (!attr) {
-        SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));
@@ -968,11 +962,8 @@ size_t umma_wgrad_scratch_floats() { return (size_t)16 << 20; }     // 64 MB
 template <int BN>
 static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
     using Cfg = WgradCfg<BN>;
-    static bool attr = false;
-    if (!attr) {
-        SIMQ_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int Cout = dY.cols, Cin = X.cols;
     const long long rows = dY.rows;
     CUtensorMap mYhi, mYlo, mXhi, mXlo;
@@ -1002,11 +993,8 @@ static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, fl
 
 static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
     using Cfg = WgradCfg<128>;
-    static bool attr = false;
-    if (!attr) {
-        SIMQ_CUDA(cudaFuncSetAttribute(wgrad2_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
-    }
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad2_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));

@@ -118,9 +118,12 @@ def _momentum_views(net: FCN, optimizer):
     if net.flat_momentum is None or net.flat_momentum.device != net.flat_params.device:
         net.flat_momentum = torch.zeros_like(net.flat_params)
         net.momentum_initialized = False
-    if getattr(net, '_momentum_bound_to', None) is optimizer:
-        return
     po = net._layout[2]
+    if getattr(net, '_momentum_bound_to', None) is optimizer:
+        p0 = net._tr_cache[0]                       # still bound?  optimizer.load_state_dict() (resume, train.py:200-210)
+        buf0 = optimizer.state[p0].get('momentum_buffer') if p0 in optimizer.state else None   # replaces the buffers
+        if buf0 is not None and buf0.data_ptr() == net.flat_momentum.data_ptr() + 4 * po[0]:
+            return
     have = 0
     for i, (_, p) in enumerate(net.trainable()):
         view = net.flat_momentum[po[i]:po[i + 1]].view(p.shape)

@@ -168,3 +168,39 @@ def test_replay_buffer_matches_reference_semantics():
     random.seed(5); x = clone.sample(3).to_transition()
     random.seed(5); y = ours.sample(3).to_transition()
     assert x.action == y.action and all(np.array_equal(p, q) for p, q in zip(x.state, y.state))
+
+
+def test_reference_checkpoint_formats_round_trip(tmp_path):
+    """policy_*.pth.tar as written by train.py:313-321 ({'timestep', 'state_dicts': [DataParallel state_dict]}) loads
+    through DQNPolicy (policies.py:25-33), and an optimizer state_dict (train.py:324, 200-210) re-binds to the flat
+    momentum vector."""
+    st = O.make_state(5, 2, 9)
+    ckpt = {'timestep': 123, 'state_dicts': [{'module.' + k: v for k, v in st.items()}]}
+    path = str(tmp_path / 'policy_00000123.pth.tar')
+    torch.save(ckpt, path)
+
+    class Cfg:
+        robot_config = [{'lifting_robot': 4}]
+        num_input_channels, batch_size, final_exploration = 5, 8, 0.01
+        checkpoint_path, policy_path = 'x', path
+    pol = policies.DQNPolicy(Cfg(), train=True, device='cpu')
+    net = pol.policy_nets[0].module
+    assert net.training and torch.equal(net.conv3.weight, st['conv3.weight']) and int(net.bn2.num_batches_tracked) == 3
+    # what our modules save is what the reference expects back
+    again = {'timestep': 124, 'state_dicts': [pol.policy_nets[0].state_dict()]}
+    torch.save(again, path)
+    back = torch.load(path, map_location='cpu')['state_dicts'][0]
+    assert list(back.keys()) == list(ckpt['state_dicts'][0].keys())
+    assert all(torch.equal(back[k], ckpt['state_dicts'][0][k]) for k in back)
+    # optimizer resume: buffers replaced by load_state_dict are copied into / re-bound to the flat momentum vector
+    opt = torch.optim.SGD(pol.policy_nets[0].parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    T._momentum_views(net, opt)
+    sd = opt.state_dict()
+    for i, stt in sd['state'].items():
+        stt['momentum_buffer'] = torch.full_like(stt['momentum_buffer'], float(i + 1))
+    opt.load_state_dict(sd)
+    T._momentum_views(net, opt)
+    po = net._layout[2]
+    assert float(net.flat_momentum[po[0]]) == 1.0 and float(net.flat_momentum[po[3]]) == 4.0 and net.momentum_initialized
+    p0 = net._tr_cache[0]
+    assert opt.state[p0]['momentum_buffer'].data_ptr() == net.flat_momentum.data_ptr()
