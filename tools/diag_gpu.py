@@ -63,7 +63,7 @@ if 'step' in parts:
                 g = r['grad_rel_l2']
                 worst = sorted(g.items(), key=lambda kv: -kv[1])[:6]
                 pw = sorted(r['param_rel_l2'].items(), key=lambda kv: -kv[1])[:3]
-                return (f"loss={r['loss']} ref={r['loss_ref']} td={r['td']} ref={r['td_ref']} gnorm={r['grad_norm']:.6g}/{r['grad_norm_ref']:.6g} "
+                return (f"FLAT_GRAD_REL_L2={r['flat_grad_rel_l2']:.3e} loss={r['loss']} ref={r['loss_ref']} td={r['td']} ref={r['td_ref']} gnorm={r['grad_norm']:.6g}/{r['grad_norm_ref']:.6g} "
                         f"bn={r['bn_err']:.2e} nbt_ok={r['nbt'] == r['nbt_ref']} fc={r['fc_untouched']} worst_grads={worst} worst_params={pw} "
                         f"mom={None if r['mom_rel_l2'] is None else max(r['mom_rel_l2'].values()):.2e}")
             guard(f'train step {bname} fused={fused}', run)
