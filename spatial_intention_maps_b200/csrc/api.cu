@@ -4,6 +4,7 @@
 #include "../../include/simq.h"
 #include "kernels.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -141,6 +142,13 @@ struct simq_ctx {
     Split dyA, dyB, dy2h, dy0s; float* stem_tmp;
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     long long launches0;
+    // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
+    struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; long long launches; uint64_t last_use; };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t side_stream; cudaEvent_t ev_in, ev_out;
+    int graph_mode;                  // -1: read SIMQ_GRAPH on first use; 0 off; 1 on
+    bool step_warm;                  // an eager step has run (function attributes set, tensor-map encoder resolved)
+    uint64_t pack_epoch, graph_clock; // pack_epoch: bumped whenever a packed-weight slot changes owner
 };
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -253,6 +261,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     e = cudaMemset(c->pool, 0, c->pool_bytes);
     if (e != cudaSuccess) { simq_set_error("simq_ctx_create: memset -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
     c->launches0 = g_simq_launches;
+    c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0;
     if (umma_init()) { cudaFree(c->pool); delete c; return 1; }
     *out = c;
     return 0;
@@ -261,6 +270,10 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
 extern "C" void simq_ctx_destroy(simq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->pool);
     delete c;
 }
@@ -302,7 +315,7 @@ static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version,
     for (int i = 0; i < 2; ++i)
         if (c->packed[i].used && c->packed[i].key == params) ps = &c->packed[i];
     if (ps && version != 0 && ps->version == version) return ps;
-    if (!ps) { ps = &c->packed[c->packed_next]; c->packed_next ^= 1; }
+    if (!ps) { ps = &c->packed[c->packed_next]; c->packed_next ^= 1; ++c->pack_epoch; }
     std::vector<ConvP> convs; conv_list(c->d, convs);
     for (size_t i = 0; i < convs.size(); ++i) {
         if (k_pack_weights(params + c->d.poff[convs[i].w], convs[i].cout, convs[i].cin, convs[i].k * convs[i].k, ps->fwd[i],
@@ -609,15 +622,11 @@ extern "C" int simq_sgd_step(simq_ctx* c, float* params, float* grads, float* mo
                       (cudaStream_t)stream);
 }
 
-extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
-                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
-                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
-                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
-                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
-    TRY(check_fwd_args(c, params, bn, s_, B));
-    if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
-    if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
-    cudaStream_t s = (cudaStream_t)stream;
+static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                           const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                           const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                           const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                           int first_step, int double_dqn, int apply_update, float* out2, cudaStream_t s) {
     int err;
     PackedSet* pw = get_packed(c, params, 0, s, &err);                                     // SGD changed them last step
     if (err) return 1;
@@ -643,6 +652,95 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
     TRY(run_backward(c, pw, params, s_, x_layout, dq, B, grads, s));
     if (apply_update)
         TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
+    return 0;
+}
+
+static inline uint64_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, s_, B));
+    if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
+    if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+#define BODY(STREAM) train_step_body(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout, \
+                                     action, reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update, out2, STREAM)
+    if (c->graph_mode < 0) { const char* e = getenv("SIMQ_GRAPH"); c->graph_mode = e ? (atoi(e) != 0) : 1; }
+    // The ~330 launches of a step are replayed as ONE CUDA graph per distinct argument tuple.  The first step of a context
+    // runs eagerly (one-time function attributes), per-kernel event profiling (simq_profile) also forces the eager path.
+    if (!c->graph_mode || g_prof_on || !c->step_warm) {
+        int rc = BODY(s);
+        if (!rc) c->step_warm = true;
+        return rc;
+    }
+    bool target_hit = false;         // would the packed target weights be reused?  (decides whether pack kernels are in the graph)
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == target_params && target_version != 0 && c->packed[i].version == target_version) target_hit = true;
+    std::vector<uint64_t> key = {(uint64_t)params, (uint64_t)bn, (uint64_t)nbt, (uint64_t)target_params, (uint64_t)target_bn,
+                                 (uint64_t)target_hit, (uint64_t)grads, (uint64_t)momentum, (uint64_t)s_, (uint64_t)s_next, (uint64_t)x_layout,
+                                 (uint64_t)action, (uint64_t)reward, (uint64_t)nonfinal, (uint64_t)B, (uint64_t)Bn, fbits(gamma), fbits(lr),
+                                 fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step, (uint64_t)double_dqn, (uint64_t)apply_update,
+                                 (uint64_t)out2, (uint64_t)c->backend, c->pack_epoch};
+    // the legacy default stream cannot be captured: run on a side stream ordered after / before it by events
+    cudaStream_t cs = s;
+    const bool side = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+    if (side) {
+        if (!c->side_stream) {
+            SIMQ_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+            SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+            SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+        }
+        cs = c->side_stream;
+        SIMQ_CUDA(cudaEventRecord(c->ev_in, s));
+        SIMQ_CUDA(cudaStreamWaitEvent(cs, c->ev_in, 0));
+    }
+    simq_ctx::GraphEntry* ge = nullptr;
+    for (auto& g : c->graphs)
+        if (g.key == key) ge = &g;
+    if (!ge) {
+        const uint64_t epoch0 = c->pack_epoch;
+        const long long l0 = g_simq_launches;
+        SIMQ_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        int rc = BODY(cs);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cs, &graph);
+        const long long captured = g_simq_launches - l0;
+        g_simq_launches = l0;                                   // nothing ran yet
+        if (rc || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            if (!rc) simq_set_error("simq_train_step: stream capture failed: %s", cudaGetErrorString(e));
+            return 1;
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { simq_set_error("simq_train_step: cudaGraphInstantiate: %s", cudaGetErrorString(e)); return 1; }
+        if (c->graphs.size() >= 8) {                            // evict the least recently used
+            size_t victim = 0;
+            for (size_t i = 1; i < c->graphs.size(); ++i)
+                if (c->graphs[i].last_use < c->graphs[victim].last_use) victim = i;
+            cudaGraphExecDestroy(c->graphs[victim].exec);
+            c->graphs.erase(c->graphs.begin() + victim);
+        }
+        if (c->pack_epoch != epoch0) key.back() = c->pack_epoch;   // the capture itself (re)assigned a weight slot
+        c->graphs.push_back({key, exec, captured, 0});
+        ge = &c->graphs.back();
+    }
+    ge->last_use = ++c->graph_clock;
+    // host-side bookkeeping the eager body would have done
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == target_params && Bn > 0) c->packed[i].version = target_version;
+    c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1;
+    SIMQ_CUDA(cudaGraphLaunch(ge->exec, cs));
+    g_simq_launches += ge->launches;
+    if (side) {
+        SIMQ_CUDA(cudaEventRecord(c->ev_out, cs));
+        SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
+    }
+#undef BODY
     return 0;
 }
 

@@ -202,6 +202,32 @@ def test_device_replay_buffer_feeds_the_same_update():
     assert torch.equal(losses[0][2], losses[1][2])
 
 
+def test_cuda_graph_replay_matches_eager(monkeypatch):
+    """simq_train_step replays the step as a CUDA graph from the second call on; six updates (two distinct
+    non-terminal counts -> two graphs, first update eager) must leave exactly the parameters, BN buffers and
+    losses of the eager launch path (SIMQ_GRAPH=0)."""
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    results = []
+    for mode in ('1', '0'):
+        monkeypatch.setenv('SIMQ_GRAPH', mode)
+        net, st = G.make_net(4, 2, 23, max_batch=8)
+        tgt = networks.FCN(4, 2, max_batch=8)
+        tgt.load_state_dict(st)
+        tgt = tgt.to(G.DEV).eval()
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        losses = []
+        for step in range(6):
+            batch = synth.synth_batch(8, 4, 2, 100 + step, terminal_every=4 if step % 2 else 8)
+            if step == 4:                                       # a target sync in between (train.py:267-269)
+                tgt.load_state_dict(net.state_dict())
+            losses.append(T.train(G.Cfg(8, 4), net, tgt, opt, batch, None, 0.75)['loss'])
+        results.append((losses, net.flat_params.clone(), net.flat_bn.clone(), net.flat_nbt.clone()))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1]) and torch.equal(results[0][2], results[1][2])
+    assert torch.equal(results[0][3], results[1][3])
+
+
 def test_policy_step_matches_golden():
     """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
     from oracle import fcn_oracle as O
