@@ -657,33 +657,19 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
 
 static inline uint64_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
-                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
-                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
-                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
-                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
-    TRY(check_fwd_args(c, params, bn, s_, B));
-    if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
-    if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
-    cudaStream_t s = (cudaStream_t)stream;
-#define BODY(STREAM) train_step_body(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout, \
-                                     action, reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update, out2, STREAM)
+// Runs `body(stream)` -- a fixed sequence of this library's launches -- as a CUDA graph: captured the first time a key
+// is seen, replayed afterwards (LRU of 8 graphs per context).  The first graphed call of a context runs eagerly
+// (one-time function attributes), and per-kernel event profiling (simq_profile) forces the eager path.
+template <typename Body, typename OnReplay>
+static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, Body body, OnReplay on_replay) {
     if (c->graph_mode < 0) { const char* e = getenv("SIMQ_GRAPH"); c->graph_mode = e ? (atoi(e) != 0) : 1; }
-    // The ~330 launches of a step are replayed as ONE CUDA graph per distinct argument tuple.  The first step of a context
-    // runs eagerly (one-time function attributes), per-kernel event profiling (simq_profile) also forces the eager path.
     if (!c->graph_mode || g_prof_on || !c->step_warm) {
-        int rc = BODY(s);
+        int rc = body(s);
         if (!rc) c->step_warm = true;
         return rc;
     }
-    bool target_hit = false;         // would the packed target weights be reused?  (decides whether pack kernels are in the graph)
-    for (int i = 0; i < 2; ++i)
-        if (c->packed[i].used && c->packed[i].key == target_params && target_version != 0 && c->packed[i].version == target_version) target_hit = true;
-    std::vector<uint64_t> key = {(uint64_t)params, (uint64_t)bn, (uint64_t)nbt, (uint64_t)target_params, (uint64_t)target_bn,
-                                 (uint64_t)target_hit, (uint64_t)grads, (uint64_t)momentum, (uint64_t)s_, (uint64_t)s_next, (uint64_t)x_layout,
-                                 (uint64_t)action, (uint64_t)reward, (uint64_t)nonfinal, (uint64_t)B, (uint64_t)Bn, fbits(gamma), fbits(lr),
-                                 fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step, (uint64_t)double_dqn, (uint64_t)apply_update,
-                                 (uint64_t)out2, (uint64_t)c->backend, c->pack_epoch};
+    key.push_back((uint64_t)c->backend);
+    key.push_back(c->pack_epoch);
     // the legacy default stream cannot be captured: run on a side stream ordered after / before it by events
     cudaStream_t cs = s;
     const bool side = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
@@ -704,20 +690,20 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
         const uint64_t epoch0 = c->pack_epoch;
         const long long l0 = g_simq_launches;
         SIMQ_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-        int rc = BODY(cs);
+        int rc = body(cs);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(cs, &graph);
         const long long captured = g_simq_launches - l0;
         g_simq_launches = l0;                                   // nothing ran yet
         if (rc || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
-            if (!rc) simq_set_error("simq_train_step: stream capture failed: %s", cudaGetErrorString(e));
+            if (!rc) simq_set_error("stream capture failed: %s", cudaGetErrorString(e));
             return 1;
         }
         cudaGraphExec_t exec = nullptr;
         e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { simq_set_error("simq_train_step: cudaGraphInstantiate: %s", cudaGetErrorString(e)); return 1; }
+        if (e != cudaSuccess) { simq_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return 1; }
         if (c->graphs.size() >= 8) {                            // evict the least recently used
             size_t victim = 0;
             for (size_t i = 1; i < c->graphs.size(); ++i)
@@ -730,18 +716,51 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
         ge = &c->graphs.back();
     }
     ge->last_use = ++c->graph_clock;
-    // host-side bookkeeping the eager body would have done
-    for (int i = 0; i < 2; ++i)
-        if (c->packed[i].used && c->packed[i].key == target_params && Bn > 0) c->packed[i].version = target_version;
-    c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1;
+    on_replay();                                                // host-side bookkeeping the eager body would have done
     SIMQ_CUDA(cudaGraphLaunch(ge->exec, cs));
     g_simq_launches += ge->launches;
     if (side) {
         SIMQ_CUDA(cudaEventRecord(c->ev_out, cs));
         SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
     }
-#undef BODY
     return 0;
+}
+
+static bool packed_hit(simq_ctx* c, const float* params, uint64_t version) {
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == params && version != 0 && c->packed[i].version == version) return true;
+    return false;
+}
+static void packed_set_version(simq_ctx* c, const float* params, uint64_t version) {
+    for (int i = 0; i < 2; ++i)
+        if (c->packed[i].used && c->packed[i].key == params) c->packed[i].version = version;
+}
+
+extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
+    TRY(check_fwd_args(c, params, bn, s_, B));
+    if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
+    if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
+    // whether the packed target weights are reused decides whether their pack kernels are part of the graph
+    const bool target_hit = packed_hit(c, target_params, target_version);
+    std::vector<uint64_t> key = {1, (uint64_t)params, (uint64_t)bn, (uint64_t)nbt, (uint64_t)target_params, (uint64_t)target_bn,
+                                 (uint64_t)target_hit, (uint64_t)grads, (uint64_t)momentum, (uint64_t)s_, (uint64_t)s_next, (uint64_t)x_layout,
+                                 (uint64_t)action, (uint64_t)reward, (uint64_t)nonfinal, (uint64_t)B, (uint64_t)Bn, fbits(gamma), fbits(lr),
+                                 fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step, (uint64_t)double_dqn, (uint64_t)apply_update,
+                                 (uint64_t)out2};
+    return run_graphed(c, key, (cudaStream_t)stream,
+        [&](cudaStream_t st) {
+            return train_step_body(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout,
+                                   action, reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update,
+                                   out2, st);
+        },
+        [&]() {
+            if (Bn > 0) packed_set_version(c, target_params, target_version);
+            c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1;
+        });
 }
 
 extern "C" int simq_gather_rows(const float* src, const int64_t* idx, int n, int64_t row_floats, float* dst, simq_stream stream) {
@@ -761,30 +780,43 @@ extern "C" int simq_intention_step(simq_ctx* c, float* params, float* bn, int64_
     TRY(check_fwd_args(c, params, bn, state, B));
     if (!grads || !momentum || !out1) { simq_set_error("simq_intention_step: NULL argument"); return 1; }
     if (c->d.A != 1) { simq_set_error("simq_intention_step: the intention net has one output channel (A=%d)", c->d.A); return 1; }
-    cudaStream_t s = (cudaStream_t)stream;
-    int err;
-    PackedSet* pw = get_packed(c, params, 0, s, &err);
-    if (err) return 1;
-    // train.py:145-148: inputs = all channels but the last, target = the last channel of the same state
-    TRY(run_forward(c, pw, params, bn, nbt, state, B, SIMQ_X_NHWC_PLUS1, 1, c->set[0], c->q_s, s));
-    TRY(k_bce_tail(c->q_s, state + c->d.C, c->d.C + 1, (long long)B * 9216, out1, c->dq, c->dpartials, s));     // :149-150
-    TRY(run_backward(c, pw, params, state, SIMQ_X_NHWC_PLUS1, c->dq, B, grads, s));                              // :151-152
-    if (apply_update)                                                                                           // :153
-        TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
-    return 0;
+    std::vector<uint64_t> key = {2, (uint64_t)params, (uint64_t)bn, (uint64_t)nbt, (uint64_t)grads, (uint64_t)momentum, (uint64_t)state,
+                                 (uint64_t)B, fbits(lr), fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step,
+                                 (uint64_t)apply_update, (uint64_t)out1};
+    return run_graphed(c, key, (cudaStream_t)stream,
+        [&](cudaStream_t s) {
+            int err;
+            PackedSet* pw = get_packed(c, params, 0, s, &err);
+            if (err) return 1;
+            // train.py:145-148: inputs = all channels but the last, target = the last channel of the same state
+            TRY(run_forward(c, pw, params, bn, nbt, state, B, SIMQ_X_NHWC_PLUS1, 1, c->set[0], c->q_s, s));
+            TRY(k_bce_tail(c->q_s, state + c->d.C, c->d.C + 1, (long long)B * 9216, out1, c->dq, c->dpartials, s));     // :149-150
+            TRY(run_backward(c, pw, params, state, SIMQ_X_NHWC_PLUS1, c->dq, B, grads, s));                              // :151-152
+            if (apply_update)                                                                                           // :153
+                TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
+            return 0;
+        },
+        [&]() { c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1; });
 }
 
 extern "C" int simq_greedy_action(simq_ctx* c, const float* params, const float* bn, const float* x, int B, int x_layout,
                                   int64_t* action_out, float* q, uint64_t params_version, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, x, B));
     if (!action_out) { simq_set_error("simq_greedy_action: action_out is NULL"); return 1; }
-    cudaStream_t s = (cudaStream_t)stream;
-    int err;
-    PackedSet* pw = get_packed(c, params, params_version, s, &err);
-    if (err) return 1;
-    float* qq = q ? q : c->q_nt;
-    TRY(run_forward(c, pw, params, (float*)bn, nullptr, x, B, x_layout, 0, c->set[1], qq, s));
-    return k_argmax_rows(qq, B, (long long)c->d.A * 9216, (long long*)action_out, s);
+    // the env loop calls this once per step with the same buffers: replay one graph (policies.py:47-74)
+    const bool hit = packed_hit(c, params, params_version);
+    std::vector<uint64_t> key = {3, (uint64_t)params, (uint64_t)bn, (uint64_t)x, (uint64_t)B, (uint64_t)x_layout, (uint64_t)action_out,
+                                 (uint64_t)q, (uint64_t)hit};
+    return run_graphed(c, key, (cudaStream_t)stream,
+        [&](cudaStream_t s) {
+            int err;
+            PackedSet* pw = get_packed(c, params, params_version, s, &err);
+            if (err) return 1;
+            float* qq = q ? q : c->q_nt;
+            TRY(run_forward(c, pw, params, (float*)bn, nullptr, x, B, x_layout, 0, c->set[1], qq, s));
+            return k_argmax_rows(qq, B, (long long)c->d.A * 9216, (long long*)action_out, s);
+        },
+        [&]() { packed_set_version(c, params, params_version); });
 }
 
 // ------------------------------------------------------------------------------------------------

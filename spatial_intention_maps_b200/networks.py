@@ -263,6 +263,35 @@ class FCN(nn.Module):
         return act, q
 
 
+    def greedy_action_hwc(self, state_hwc, want_q: bool = False):
+        """One environment step's action for a single (96,96,C) float32 state (policies.py:56-64): pinned staging ->
+        persistent device buffers -> eval forward + arg-max replayed as ONE CUDA graph -> the action index (8 bytes)
+        back.  Returns (int action, Q-map ndarray (A,96,96) or None)."""
+        import numpy as np
+        dev = self.flat_params.device
+        c = self.ctx(1)
+        st = self.__dict__.get('_ga')
+        if st is None or st['dev'] != dev:
+            Cn, A = self.num_input_channels, self.num_output_channels
+            st = {'dev': dev, 'pin': torch.empty((1, 96, 96, Cn), dtype=torch.float32, pin_memory=True),
+                  'x': torch.empty((1, 96, 96, Cn), dtype=torch.float32, device=dev),
+                  'act': torch.zeros(1, dtype=torch.int64, device=dev),
+                  'act_host': torch.zeros(1, dtype=torch.int64, pin_memory=True),
+                  'q': torch.empty((1, A, 96, 96), dtype=torch.float32, device=dev)}
+            self.__dict__['_ga'] = st
+        if state_hwc.shape != tuple(st['pin'].shape[1:]):
+            raise ValueError(f'expected a {tuple(st["pin"].shape[1:])} state, got {state_hwc.shape}')
+        st['pin'].numpy()[0] = np.asarray(state_hwc, dtype=np.float32)
+        st['x'].copy_(st['pin'], non_blocking=True)
+        _lib.check(_lib.lib().simq_greedy_action(c.handle, _lib.ptr(self.flat_params), _lib.ptr(self.flat_bn), _lib.ptr(st['x']), 1,
+                                                 _lib.X_NHWC, _lib.ptr(st['act']), _lib.ptr(st['q']) if want_q else None,
+                                                 self.params_version, _lib.stream_ptr()), 'simq_greedy_action')
+        st['act_host'].copy_(st['act'], non_blocking=True)
+        q = st['q'][0].cpu().numpy() if want_q else None
+        torch.cuda.current_stream().synchronize()
+        return int(st['act_host'][0]), q
+
+
 class SingleDeviceParallel(nn.Module):
     """Stands in for the ``torch.nn.DataParallel`` wrapper of policies.py:39-41: keeps the ``module.``
     state_dict prefix of reference checkpoints, but never replicates -- this framework is one

@@ -96,16 +96,15 @@ class DQNPolicy:
                 net.eval()
                 for j, s in enumerate(g):
                     if s is not None:
-                        x = self._to_device_nhwc(s)
-                        explore = random.random() < exploration_eps
-                        a_dev, q = net.module.greedy_action(x, want_q=debug)
+                        explore = random.random() < exploration_eps        # same RNG consumption order as policies.py:61-62
                         if explore:
                             a = random.randrange(VectorEnv.get_action_space(robot_type))
+                            q = net.module.greedy_action_hwc(s, want_q=True)[1] if debug else None
                         else:
-                            a = int(a_dev.item())
+                            a, q = net.module.greedy_action_hwc(s, want_q=debug)
                         action[i][j] = a
-                        if debug:                       # the reference copies the Q-map to the host every
-                            output[i][j] = q[0].cpu().numpy()   # step (policies.py:66); only done on request here
+                        if debug:                       # the reference copies the Q-map to the host every step
+                            output[i][j] = q            # (policies.py:66); only done on request here
                 if self.train:
                     net.train()
 
