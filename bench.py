@@ -249,7 +249,7 @@ def run_simq(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16x2-split operands (hi+lo, 3 tcgen05 MMAs per product), f32 accumulate/activations-in-f32-precision',
+            'dtype': 'bf16 hi+lo split operands (3 tcgen05 MMAs per product), f32 accumulate',
             'data': 'synthetic',
             'config': {'workload': workload_name(B), 'global_batch': world * B, 'parallelism': f'dp{world}',
                        'l2': 'no flush: a step streams >3 GB of activations per GPU through the 126 MB L2, evicting the 47 MB batch',

@@ -362,7 +362,7 @@ static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Spli
 }
 
 static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* bn, int64_t* nbt, const float* x, int B,
-                       int x_layout, int training, ActSet& S, float* q, cudaStream_t s) {
+                       int x_layout, int training, ActSet& S, float* q, cudaStream_t s, bool reuse_acol = false) {
     const NetDesc& d = c->d;
     const long long R25 = (long long)B * IMG25, R48 = (long long)B * 2304;
     const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
@@ -370,7 +370,7 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     S.valid = false;
     // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
     if (be == SIMQ_BACKEND_UMMA) {
-        TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));
+        if (!reuse_acol) TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));     // else: same input as the previous pass on S
         TRY(conv_bn(c, S, S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, s));
     } else {
         TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
@@ -638,7 +638,8 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
         // train.py:122/124  target forward, eval-mode BN
         PackedSet* pt = get_packed(c, target_params, target_version, s, &err);
         if (err) return 1;
-        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, s));
+        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, s,
+                        /*reuse_acol=*/double_dqn != 0));     // the online pass just expanded the same s' into set[1]
         pw = nullptr;
         for (int i = 0; i < 2; ++i)
             if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];

@@ -317,61 +317,63 @@ int k_stem_wgrad(const float* x, int x_layout, int B, int C, const float* dy0, f
 
 // ------------------------------------------------------------------------------------------
 // stem on the tensor cores: im2col of the 7x7/2 windows into a split-bf16 [B*2304][Kp] matrix
-// (column j = c*49 + ky*7 + kx, the OIHW flattening of resnet18.conv1.weight; Kp = 49*C rounded up to
-// 64, zero padded) so that conv1 and its weight gradient are plain GEMMs for the tcgen05 kernels.
+// (column j = (ky*7 + kx)*C + c -- tap-major, channel-minor, so that with NHWC input the 8 columns a thread
+// writes are an almost contiguous run of the input window; Kp = 49*C rounded up to 64, zero padded) so
+// that conv1 and its weight gradient are plain GEMMs for the tcgen05 kernels.  k_pack_stem / k_strip_stem
+// translate between this column order and the OIHW flattening (c*49 + tap) of resnet18.conv1.weight.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, int layout, int B, int C, int Kp, Split acol) {
-    const int G = Kp >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * 2304 * G;
-    if (idx >= total) return;
-    const int g = (int)(idx % G);
-    const long long p = idx / G;
-    const int n = (int)(p / 2304), r = (int)(p % 2304), oy = r / 48, ox = r % 48;
+    const unsigned G = (unsigned)Kp >> 3;               // 32-bit index arithmetic (host checks B*2304*G < 2^32)
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)B * 2304u * G) return;
+    const unsigned p = idx / G;
+    const int g = (int)(idx - p * G);
+    const int n = (int)(p / 2304u), r = (int)(p - (unsigned)n * 2304u), oy = r / 48, ox = r - oy * 48;
     const int NJ = C * 49;
     float v[8];
+    int tap = (g * 8) / C, c = g * 8 - tap * C;          // one division per thread; (tap, c) advance incrementally
+    int ky = tap / 7, kx = tap - ky * 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        int j = g * 8 + i;
-        float t = 0.f;
-        if (j < NJ) {
-            int c = j / 49, tap = j - c * 49, ky = tap / 7, kx = tap - ky * 7;
-            t = stem_x(x, layout, C, n, c, 2 * oy + ky - 3, 2 * ox + kx - 3);
-        }
-        v[i] = t;
+        v[i] = (g * 8 + i < NJ) ? stem_x(x, layout, C, n, c, 2 * oy + ky - 3, 2 * ox + kx - 3) : 0.f;
+        if (++c == C) { c = 0; if (++kx == 7) { kx = 0; ++ky; } }
     }
     store8_split(acol, (size_t)p * Kp + g * 8, v);
 }
 
 int k_stem_im2col(const float* x, int x_layout, int B, int C, int Kp, Split acol, cudaStream_t s) {
     long long n = (long long)B * 2304 * (Kp / 8);
+    if (n >= (1LL << 32)) { simq_set_error("k_stem_im2col: batch too large for 32-bit indexing"); return 1; }
     stem_im2col_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x, x_layout, B, C, Kp, acol);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
 
 // w OIHW [64][C*49] f32 -> split [64][Kp], zero padded
-__global__ void pack_stem_kernel(const float* __restrict__ w, int NJ, int Kp, Split out) {
+__global__ void pack_stem_kernel(const float* __restrict__ w, int C, int Kp, Split out) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 64 * Kp) return;
+    const int NJ = C * 49;
     int co = idx / Kp, j = idx % Kp;
-    float v = j < NJ ? w[co * NJ + j] : 0.f;
+    int tap = j / C, c = j - tap * C;
+    float v = j < NJ ? w[co * NJ + c * 49 + tap] : 0.f;
     split_store(v, out.hi[idx], out.lo[idx]);
 }
 int k_pack_stem(const float* w, int C, int Kp, Split out, cudaStream_t s) {
-    pack_stem_kernel<<<ceil_div(64 * Kp, 256), 256, 0, s>>>(w, C * 49, Kp, out);
+    pack_stem_kernel<<<ceil_div(64 * Kp, 256), 256, 0, s>>>(w, C, Kp, out);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
 // dW [64][C*49] <- tmp [64][Kp]
-__global__ void strip_stem_kernel(const float* __restrict__ tmp, int NJ, int Kp, float* __restrict__ dW) {
+__global__ void strip_stem_kernel(const float* __restrict__ tmp, int C, int Kp, float* __restrict__ dW) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int NJ = C * 49;
     if (idx >= 64 * NJ) return;
-    int co = idx / NJ, j = idx % NJ;
-    dW[idx] = tmp[co * Kp + j];
+    int co = idx / NJ, r = idx % NJ, c = r / 49, tap = r - c * 49;     // OIHW element (co, c, tap)
+    dW[idx] = tmp[co * Kp + tap * C + c];
 }
 int k_strip_stem(const float* tmp, int C, int Kp, float* dW, cudaStream_t s) {
-    strip_stem_kernel<<<ceil_div(64 * C * 49, 256), 256, 0, s>>>(tmp, C * 49, Kp, dW);
+    strip_stem_kernel<<<ceil_div(64 * C * 49, 256), 256, 0, s>>>(tmp, C, Kp, dW);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
