@@ -36,6 +36,10 @@ typedef void* simq_stream;            /* cudaStream_t */
 /* conv back-end: the tcgen05/TMA kernels are the product; the FMA kernels are an on-device
  * fp32 comparator for tests/debug (never the default). */
 enum { SIMQ_BACKEND_UMMA = 0, SIMQ_BACKEND_FMA = 1 };
+/* tensor-core operand precision.  PARITY (default): every operand is a bf16 hi+lo pair and every product
+ * three MMAs (meets the 1e-3 Q-map / arg-max bar).  BF16: hi planes only, one MMA per product -- ~2.5x faster
+ * conv kernels, Q-map error ~1e-2 (FAILS the parity bar; opt-in for users who train in bf16 anyway). */
+enum { SIMQ_PRECISION_PARITY = 0, SIMQ_PRECISION_BF16 = 1 };
 /* x layouts accepted by the stem */
 /* SIMQ_X_NHWC_PLUS1: [B,96,96,C+1] whose last channel is NOT a network input (train.py:145-146) */
 enum { SIMQ_X_NCHW = 0, SIMQ_X_NHWC = 1, SIMQ_X_NHWC_PLUS1 = 2 };
@@ -52,6 +56,7 @@ int simq_layout(int C, int A, int64_t* n_params, int64_t* n_bn, int64_t* param_o
 int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch);
 void simq_ctx_destroy(simq_ctx*);
 int simq_set_backend(simq_ctx*, int backend);
+int simq_set_precision(simq_ctx*, int mode);
 size_t simq_workspace_bytes(const simq_ctx*);
 
 /* Replaces FCN.forward (networks.py:16-26).  x: f32 [B,C,96,96] (NCHW) or [B,96,96,C] (NHWC);

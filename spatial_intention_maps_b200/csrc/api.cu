@@ -132,6 +132,7 @@ struct PackedSet {                   // split-bf16 shadows of the conv weights o
 
 struct simq_ctx {
     int device, maxB, backend;
+    int terms;                       // 3 = parity mode (default), 1 = bf16 fast mode (simq_set_precision)
     NetDesc d;
     char* pool; size_t pool_bytes, pool_used;
     ActSet set[2];
@@ -250,7 +251,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     SIMQ_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { simq_set_error("simq_ctx_create: device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor); return 2; }
     simq_ctx* c = new simq_ctx();
-    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA;
+    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = 3;
     build_desc(c->d, C, A);
     c->pool = nullptr;
     carve_all(c, true);
@@ -283,6 +284,12 @@ extern "C" int simq_set_backend(simq_ctx* c, int backend) {
     c->backend = backend;
     return 0;
 }
+extern "C" int simq_set_precision(simq_ctx* c, int mode) {
+    if (!c || (mode != SIMQ_PRECISION_PARITY && mode != SIMQ_PRECISION_BF16)) { simq_set_error("simq_set_precision: bad argument"); return 1; }
+    c->terms = mode == SIMQ_PRECISION_BF16 ? 1 : 3;
+    ++c->pack_epoch;                 // invalidates captured graphs (the key carries pack_epoch)
+    return 0;
+}
 extern "C" size_t simq_workspace_bytes(const simq_ctx* c) { return c ? c->pool_bytes : 0; }
 extern "C" int64_t simq_launch_count(const simq_ctx* c) { return c ? (int64_t)(g_simq_launches - c->launches0) : 0; }
 
@@ -296,6 +303,7 @@ static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Sp
                     ConvEpilogue ep, cudaStream_t s) {
     if (backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
         UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
+        ep.terms = c->terms;
         return k_conv_umma(a, w, N, ntaps, out, ep, s);
     }
     return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, s);
@@ -304,7 +312,7 @@ static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows
                      cudaStream_t s) {
     if (backend == SIMQ_BACKEND_UMMA && umma_wgrad_supported(Cout, Cin)) {
         UmmaTensor y{dY, rows, Cout}, x{X, rows, Cin};
-        return k_wgrad_umma(y, x, ntaps, dW, c->wscratch, s);
+        return k_wgrad_umma(y, x, ntaps, dW, c->wscratch, c->terms, s);
     }
     return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, c->wscratch, s);
 }

@@ -132,18 +132,22 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 // BK = 64: 128-byte K rows, SWIZZLE_128B.  BK = 32: 64-byte K rows, SWIZZLE_64B -- used with BN = 256, where a
 // 64-wide stage would be 96 KB and only two would fit: four 48 KB stages hide the TMA latency better.
-template <int BN>
+// TERMS = 3: split-bf16 operands, lo*hi + hi*lo + hi*hi (parity mode).  TERMS = 1: hi planes only, one MMA per
+// product (plain bf16 "fast" mode: ~3x less tensor work, fails the 1e-3 Q-map bar -- opt-in, see simq_set_precision).
+template <int BN, int TERMS = 3>
 struct ConvCfg {
     static constexpr int BK = 64;
     static constexpr int A_BYTES = UM_BM * BK * 2;            // one plane of the A tile
     static constexpr int W_BYTES = BN * BK * 2;               // one plane of the W tile
     static constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;    // SmemDescriptor layout_type
     static constexpr uint32_t SBO = BK == 64 ? 1024u : 512u;  // 8 rows of BK*2 bytes
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_OFF = PLANES * A_BYTES;            // stage layout: A hi [, A lo], W hi [, W lo]
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4; // per epilogue warp: 32 rows x 32 columns fp32
     static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - FIXED) / STAGE_BYTES;
+    static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
@@ -273,12 +277,12 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
     }
 }
 
-template <int BN, int FL>
+template <int BN, int FL, int TERMS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
                  int N, int ntaps, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, TERMS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -324,9 +328,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
                     const int arow = m0 + off;
                     tma_load_2d(sa, &mAhi, full_bar(s), kc * BK, arow);
-                    tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * BK, arow);
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES, &mWhi, full_bar(s), kc * BK, t * N + n0);
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, full_bar(s), kc * BK, t * N + n0);
+                    tma_load_2d(sa + Cfg::W_OFF, &mWhi, full_bar(s), kc * BK, t * N + n0);
+                    if (TERMS == 3) {
+                        tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * BK, arow);
+                        tma_load_2d(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, full_bar(s), kc * BK, t * N + n0);
+                    }
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -347,12 +353,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t a_hi = umma_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
-                        tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
-                        tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                        const uint64_t w_hi = umma_desc(sa + Cfg::W_OFF + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        if (TERMS == 3) {
+                            const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                            tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                            tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else {
+                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                        }
                     }
                     tc_commit(empty_bar(s));            // frees the stage once these MMAs have read it
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
@@ -419,25 +429,28 @@ __device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc,
         : "memory");
 }
 
+template <int TERMS>
 struct Conv2Cfg {
     static constexpr int BN = 256;                            // pair tile: 256 rows x 256 columns
     static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // this CTA's 128 A rows, one plane (16 KB)
     static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of the W tile, one plane (16 KB)
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_OFF = PLANES * A_BYTES;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
     static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = TERMS == 3 ? 3 : 6;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
 };
 
-template <int FL>
+template <int FL, int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                   const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
                   int N, int ntaps, int m2_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
-    using Cfg = Conv2Cfg;
+    using Cfg = Conv2Cfg<TERMS>;
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -489,9 +502,11 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                     const uint32_t fb = mapa_rank0(full_bar(s));
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
                     tma_load_2d_cg2(sa, &mAhi, fb, kc * UM_BK, m0 + off);
-                    tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 + off);
-                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES, &mWhi, fb, kc * UM_BK, t * N + wn0);
-                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
+                    tma_load_2d_cg2(sa + Cfg::W_OFF, &mWhi, fb, kc * UM_BK, t * N + wn0);
+                    if (TERMS == 3) {
+                        tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 + off);
+                        tma_load_2d_cg2(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
+                    }
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -512,12 +527,16 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < UM_BK / 16; ++k) {
                         const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
-                        const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
-                        const uint64_t w_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 32, 16, 1024);
-                        const uint64_t w_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::W_BYTES + k * 32, 16, 1024);
-                        tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
-                        tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
-                        tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                        const uint64_t w_hi = umma_desc(sa + Cfg::W_OFF + k * 32, 16, 1024);
+                        if (TERMS == 3) {
+                            const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
+                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, 1024);
+                            tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else {
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                        }
                     }
                     tc_commit_mc2(empty_bar(s));
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
@@ -549,21 +568,23 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // wgrad: partial[z][co][ci] = sum_{p in split} dY[p][co] * X[p + off_t][ci],  z = split*ntaps + t
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int TERMS = 3>
 struct WgradCfg {
     static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // dY plane: 2 blocks of [64 rows][64 co]
     static constexpr int B_BYTES = BN * UM_BK * 2;            // X plane: BN/64 blocks of [64 rows][64 ci]
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int B_OFF = PLANES * A_BYTES;            // stage layout: dY hi [, dY lo], X hi [, X lo]
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int TERMS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
                   const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo, long long rows, int Cout,
                   int Cin, int ntaps, int nsplit, long long chunk, float* __restrict__ partial) {
-    using Cfg = WgradCfg<BN>;
+    using Cfg = WgradCfg<BN, TERMS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -605,12 +626,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < UM_BM / 64; ++j) {
                     tma_load_2d(sa + j * 8192, &mYhi, full_bar(s), co0 + j * 64, p0);
-                    tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &mYlo, full_bar(s), co0 + j * 64, p0);
+                    if (TERMS == 3) tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &mYlo, full_bar(s), co0 + j * 64, p0);
                 }
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) {
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES + j * 8192, &mXhi, full_bar(s), ci0 + j * 64, p0 + off);
-                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * 8192, &mXlo, full_bar(s), ci0 + j * 64, p0 + off);
+                    tma_load_2d(sa + Cfg::B_OFF + j * 8192, &mXhi, full_bar(s), ci0 + j * 64, p0 + off);
+                    if (TERMS == 3) tma_load_2d(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, full_bar(s), ci0 + j * 64, p0 + off);
                 }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
@@ -628,12 +649,16 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
                     // MN-major SWIZZLE_128B: 8 rows of 128 B per atom (SBO = 1024 B between 8-row groups along
                     // K), 64-channel blocks 8 KB apart (LBO); a K=16 step is two atoms = 2048 B.
                     const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
-                    const uint64_t x_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 2048, 8192, 1024);
-                    const uint64_t x_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                    tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
-                    tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
-                    tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                    const uint64_t x_hi = umma_desc(sa + Cfg::B_OFF + k * 2048, 8192, 1024);
+                    if (TERMS == 3) {
+                        const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
+                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                        tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
+                        tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
+                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                    } else {
+                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                    }
                 }
                 tc_commit(empty_bar(s));
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
@@ -674,12 +699,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
 
 // CTA-pair wgrad (Cout % 256 == 0 and Cin % 256 == 0): the pair owns a 256 (co) x 256 (ci) tile of one tap / row split;
 // each CTA stages its own 128 dY channels and half (128) of the X channels, the leader issues M = 256, N = 256 MMAs.
-template <int DUMMY>
+template <int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
                    const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo, long long rows, int Cout,
                    int Cin, int ntaps, int nsplit, long long chunk, float* __restrict__ partial) {
-    using Cfg = WgradCfg<128>;                     // per-CTA stage: 128 co + 128 ci, hi and lo = 64 KB
+    using Cfg = WgradCfg<128, TERMS>;              // per-CTA stage: 128 co + 128 ci (hi and lo: 64 KB)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -728,9 +753,11 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     tma_load_2d_cg2(sa + j * 8192, &mYhi, fb, co0 + j * 64, p0);
-                    tma_load_2d_cg2(sa + Cfg::A_BYTES + j * 8192, &mYlo, fb, co0 + j * 64, p0);
-                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + j * 8192, &mXhi, fb, ci0 + j * 64, p0 + off);
-                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * 8192, &mXlo, fb, ci0 + j * 64, p0 + off);
+                    tma_load_2d_cg2(sa + Cfg::B_OFF + j * 8192, &mXhi, fb, ci0 + j * 64, p0 + off);
+                    if (TERMS == 3) {
+                        tma_load_2d_cg2(sa + Cfg::A_BYTES + j * 8192, &mYlo, fb, co0 + j * 64, p0);
+                        tma_load_2d_cg2(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, fb, ci0 + j * 64, p0 + off);
+                    }
                 }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
@@ -746,12 +773,16 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < UM_BK / 16; ++k) {
                     const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
-                    const uint64_t x_hi = umma_desc(sa + 2 * Cfg::A_BYTES + k * 2048, 8192, 1024);
-                    const uint64_t x_lo = umma_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                    tc_mma_bf16_cg2(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
-                    tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, 1);
-                    tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
+                    const uint64_t x_hi = umma_desc(sa + Cfg::B_OFF + k * 2048, 8192, 1024);
+                    if (TERMS == 3) {
+                        const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
+                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                        tc_mma_bf16_cg2(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
+                        tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, 1);
+                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
+                    } else {
+                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                    }
                 }
                 tc_commit_mc2(empty_bar(s));
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
@@ -839,11 +870,11 @@ static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, i
 
 static int g_num_sms = 0;
 
-template <int BN, int FL>
+template <int BN, int FL, int TERMS>
 static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));
@@ -859,17 +890,17 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
     // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
-    conv_umma_kernel<BN, FL><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
+    conv_umma_kernel<BN, FL, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
 
-template <int FL>
+template <int FL, int TERMS>
 static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
-    using Cfg = Conv2Cfg;
+    using Cfg = Conv2Cfg<TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));
@@ -884,7 +915,7 @@ static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int nta
     if (m2_tiles * n_tiles < clusters) clusters = m2_tiles * n_tiles;
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
-    conv2_umma_kernel<FL><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m2_tiles,
+    conv2_umma_kernel<FL, TERMS><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m2_tiles,
                                                                         n_tiles, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
@@ -905,7 +936,9 @@ static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     if (ep.out_split.hi) fl |= EF_SPLIT;
     if (ep.bn_raw) fl |= EF_BNBWD;
     switch (fl) {
-#define CASE(F) case (F): return PAIR ? launch_conv2<(F)>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F)>(A, W, N, ntaps, out, ep, s)
+#define CASE(F) case (F):                                                                                                   \
+        if (ep.terms == 1) return PAIR ? launch_conv2<(F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 1>(A, W, N, ntaps, out, ep, s); \
+        return PAIR ? launch_conv2<(F), 3>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 3>(A, W, N, ntaps, out, ep, s)
         CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
         CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
         CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
@@ -959,11 +992,11 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
 
 size_t umma_wgrad_scratch_floats() { return (size_t)16 << 20; }     // 64 MB
 
-template <int BN>
+template <int BN, int TERMS>
 static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
-    using Cfg = WgradCfg<BN>;
+    using Cfg = WgradCfg<BN, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<BN, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int Cout = dY.cols, Cin = X.cols;
     const long long rows = dY.rows;
     CUtensorMap mYhi, mYlo, mXhi, mXlo;
@@ -981,7 +1014,7 @@ static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, fl
     long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(ceil_div(Cout, UM_BM), Cin / BN, ntaps * nsplit);
     prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s);
-    wgrad_umma_kernel<BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk,
+    wgrad_umma_kernel<BN, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk,
                                                                   scratch);
     SIMQ_LAUNCH_CHECK();
     long long n = (long long)per_split;
@@ -991,10 +1024,11 @@ static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, fl
     return 0;
 }
 
+template <int TERMS>
 static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
-    using Cfg = WgradCfg<128>;
+    using Cfg = WgradCfg<128, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad2_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad2_umma_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (!g_num_sms) {
         int dev = 0;
         SIMQ_CUDA(cudaGetDevice(&dev));
@@ -1024,7 +1058,7 @@ static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, f
     long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(2 * (Cout / 256), Cin / 256, ntaps * nsplit);
     prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s);
-    wgrad2_umma_kernel<0><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk, scratch);
+    wgrad2_umma_kernel<TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk, scratch);
     SIMQ_LAUNCH_CHECK();
     wgrad_reduce_kernel<<<ceil_div((long long)per_split, 256), 256, 0, s>>>(scratch, Cout, Cin, ntaps, nsplit, dW);
     prof_mark(PROF_WGRAD, false, 0, s);
@@ -1032,7 +1066,7 @@ static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, f
     return 0;
 }
 
-int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s) {
+int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, int terms, cudaStream_t s) {
     if (umma_init()) return 1;
     if (!umma_wgrad_supported(dY.cols, X.cols) || dY.rows != X.rows) {
         simq_set_error("k_wgrad_umma: unsupported shape Cout=%d Cin=%d", dY.cols, X.cols);
@@ -1040,7 +1074,9 @@ int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW
     }
     static int pair = -1;
     if (pair < 0) { const char* e = getenv("SIMQ_WGRAD_PAIR"); pair = e ? atoi(e) : 1; }
-    if (pair && dY.cols % 256 == 0 && X.cols % 256 == 0) return launch_wgrad2(dY, X, ntaps, dW, scratch, s);
-    if (X.cols % 128 == 0) return launch_wgrad<128>(dY, X, ntaps, dW, scratch, s);
-    return launch_wgrad<64>(dY, X, ntaps, dW, scratch, s);
+    if (pair && dY.cols % 256 == 0 && X.cols % 256 == 0)
+        return terms == 1 ? launch_wgrad2<1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad2<3>(dY, X, ntaps, dW, scratch, s);
+    if (X.cols % 128 == 0)
+        return terms == 1 ? launch_wgrad<128, 1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad<128, 3>(dY, X, ntaps, dW, scratch, s);
+    return terms == 1 ? launch_wgrad<64, 1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad<64, 3>(dY, X, ntaps, dW, scratch, s);
 }

@@ -85,12 +85,13 @@ struct ConvEpilogue {
     // BatchNorm-backward statistics of the gradient this launch produces (dgrad): with dz = out * [bn_mask > 0],
     // stats rows become (sum dz, sum dz * (bn_raw - mean) * invstd) -- saves the separate reduction pass
     const float* bn_raw; const bf16* bn_mask; const float* bn_mean; const float* bn_invstd;
+    int terms;                // 3: split-bf16 parity mode (lo*hi + hi*lo + hi*hi); 1: bf16 fast mode (hi*hi only)
 };
 static inline ConvEpilogue conv_ep(int pitch25) {
     ConvEpilogue e;
     e.pitch25 = pitch25; e.add_prev = nullptr; e.add_g = nullptr; e.add_g_mask = nullptr; e.scale = nullptr; e.shift = nullptr;
     e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
-    e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr;
+    e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr; e.terms = 3;
     return e;
 }
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
@@ -113,7 +114,7 @@ struct UmmaTensor {          // a split tensor plus its row count / width, enoug
     Split t; long long rows; int cols;
 };
 int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
-int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, cudaStream_t s);
+int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, int terms, cudaStream_t s);
 int umma_init();             // resolves cuTensorMapEncodeTiled
 bool umma_conv_supported(int K, int N);
 int umma_conv_m_tiles(long long rows);     // rows of ConvEpilogue::stats written by k_conv_umma

@@ -190,10 +190,22 @@ class FCN(nn.Module):
             self.max_batch = max(self.max_batch, batch)
             self._ctx = _lib.Ctx(dev.index if dev.index is not None else torch.cuda.current_device(),
                                  self.num_input_channels, self.num_output_channels, self.max_batch)
+            if getattr(self, '_backend', None) is not None:          # settings survive a workspace re-allocation
+                _lib.check(_lib.lib().simq_set_backend(self._ctx.handle, self._backend), 'simq_set_backend')
+            if getattr(self, '_precision', None) is not None:
+                _lib.check(_lib.lib().simq_set_precision(self._ctx.handle, self._precision), 'simq_set_precision')
         return self._ctx
 
     def set_backend(self, backend: int):
+        self._backend = backend
         _lib.check(_lib.lib().simq_set_backend(self.ctx().handle, backend), 'simq_set_backend')
+
+    def set_precision(self, mode: str):
+        """'parity' (default: split-bf16 operands, 3 MMAs per product, meets the reference-parity bar) or 'bf16'
+        (one MMA per product: ~2.5x faster conv kernels, Q-map error ~1e-2 -- does NOT meet the parity bar)."""
+        m = {'parity': _lib.PRECISION_PARITY, 'bf16': _lib.PRECISION_BF16}[mode]
+        self._precision = m
+        _lib.check(_lib.lib().simq_set_precision(self.ctx().handle, m), 'simq_set_precision')
 
     @staticmethod
     def _x_layout(x):

@@ -228,6 +228,26 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     assert torch.equal(results[0][3], results[1][3])
 
 
+def test_bf16_mode_is_characterised_and_not_default():
+    """simq_set_precision(BF16) -- one MMA per product -- is opt-in: its Q-map error is of the order SURVEY.md
+    §7.2-1 predicts for bf16 operands (1e-2: outside the 1e-3 parity bar), the default mode is untouched by it."""
+    net, st = G.make_net(5, 2, 105, max_batch=4)
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import synth
+    x = O.hwc_to_nchw(list(synth.synth_states(4, 5, 105)))
+    with torch.no_grad():
+        ref = O.forward(O.clone_state(st), x, False)
+        net.eval()
+        q_parity = net(x.to(G.DEV)).cpu()
+        net.set_precision('bf16')
+        q_bf16 = net(x.to(G.DEV)).cpu()
+        net.set_precision('parity')
+        q_again = net(x.to(G.DEV)).cpu()
+    assert G.relerr(q_parity, ref) <= QTOL and torch.equal(q_parity, q_again)
+    e = G.relerr(q_bf16, ref)
+    assert 1e-3 < e < 1e-1, e
+
+
 def test_policy_step_matches_golden():
     """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
     from oracle import fcn_oracle as O
