@@ -150,6 +150,8 @@ struct simq_ctx {
     int graph_mode;                  // -1: read SIMQ_GRAPH on first use; 0 off; 1 on
     bool step_warm;                  // an eager step has run (function attributes set, tensor-map encoder resolved)
     uint64_t pack_epoch, graph_clock; // pack_epoch: bumped whenever a packed-weight slot changes owner
+    int graph_misses;                // consecutive captures without a replay: a caller whose arguments change every call
+                                     // (e.g. a per-step learning-rate schedule) is better served by eager launches
 };
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -262,7 +264,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     e = cudaMemset(c->pool, 0, c->pool_bytes);
     if (e != cudaSuccess) { simq_set_error("simq_ctx_create: memset -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
     c->launches0 = g_simq_launches;
-    c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0;
+    c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0; c->graph_misses = 0;
     if (umma_init()) { cudaFree(c->pool); delete c; return 1; }
     *out = c;
     return 0;
@@ -695,6 +697,16 @@ static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, B
     simq_ctx::GraphEntry* ge = nullptr;
     for (auto& g : c->graphs)
         if (g.key == key) ge = &g;
+    if (ge) c->graph_misses = 0;
+    else if (++c->graph_misses > 16) {                          // never replays: stop paying for capture + instantiate
+        c->graph_mode = 0;
+        int rc = body(cs);
+        if (side && !rc) {
+            SIMQ_CUDA(cudaEventRecord(c->ev_out, cs));
+            SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
+        }
+        return rc;
+    }
     if (!ge) {
         const uint64_t epoch0 = c->pack_epoch;
         const long long l0 = g_simq_launches;
