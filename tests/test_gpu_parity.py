@@ -104,10 +104,10 @@ def _check_grads(r):
     assert abs(r['grad_norm'] - gn) <= 2e-3 * gn
 
 
-@pytest.mark.parametrize('key', ['c1', 'c2', 'traj'])
+@pytest.mark.parametrize('key', ['c1', 'c2', 'c3', 'traj'])
 @pytest.mark.parametrize('fused', [True, False], ids=['fused', 'autograd'])
 def test_dqn_step_matches_oracle_and_golden(key, fused):
-    """c1 / c2 of BASELINE.json and a 3-step trajectory; the golden losses come from the reference's own
+    """c1 / c2 / c3 (the full-size bench workload: B=128, C=5, A=1) of BASELINE.json and a 3-step trajectory; the golden losses come from the reference's own
     train.train (tests/golden/steps.npz)."""
     g = np.load(os.path.join(GOLD, 'steps.npz'))
     C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
@@ -248,6 +248,28 @@ def test_bf16_mode_is_characterised_and_not_default():
     assert 1e-3 < e < 1e-1, e
 
 
+def test_intention_policy_step_matches_oracle():
+    """policies.DQNIntentionPolicy.step (policies.py:76-146) in evaluation mode: the predicted intention map
+    sigmoid(FCN(C-1 -> 1)(s)) is appended to the state and the greedy action taken on the C-channel result."""
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import policies, synth
+    C = 5
+    pol = policies.DQNIntentionPolicy(G.Cfg(4, C), train=False)
+    st_q, st_i = O.make_state(C, 2, 51), O.make_state(C - 1, 1, 52)
+    pol.policy_nets[0].module.load_state_dict(st_q)
+    pol.intention_nets[0].module.load_state_dict(st_i)
+    for k in range(3):
+        s = synth.synth_states(1, C - 1, 60 + k)[0]
+        a, info = pol.step([[s]], exploration_eps=0.0, debug=True)
+        with torch.no_grad():
+            pred = torch.sigmoid(O.forward(O.clone_state(st_i), O.hwc_to_nchw([s]), False))[0, 0].numpy()
+        assert np.abs(info['output_intention'][0][0] - pred).max() <= 1e-3
+        a_ref, q_ref = O.greedy_action(O.clone_state(st_q), np.concatenate([s, pred[:, :, None]], axis=2))
+        assert G.relerr(torch.from_numpy(info['output'][0][0]), torch.from_numpy(q_ref)) <= QTOL
+        if a[0][0] != a_ref:
+            assert q_ref.reshape(-1)[a_ref] - q_ref.reshape(-1)[a[0][0]] <= 1e-6 * np.abs(q_ref).max()
+
+
 def test_policy_step_matches_golden():
     """policies.DQNPolicy.step greedy action == the reference's on 16 states."""
     from oracle import fcn_oracle as O
@@ -264,6 +286,18 @@ def test_policy_step_matches_golden():
         if a[0][0] != int(g['actions'][i]):          # near-tie policy
             ref_q = O.greedy_action(O.make_state(C, A, seed), states[i])[1].reshape(-1)
             assert ref_q[int(g['actions'][i])] - ref_q[a[0][0]] <= 1e-6 * np.abs(ref_q).max()
+
+
+def test_forward_full_batch128_matches_oracle():
+    """c3 at its full size (B=128, C=5, A=1; M = 80000 rows -> the CTA-pair kernels with all 74 pairs busy): the
+    train-mode Q-map against the CPU oracle directly, plus BN running statistics."""
+    errs, q, qr, bn = G.forward_trace_check(5, 1, 128, 13, True)
+    assert errs['q'] <= QTOL, errs['q']
+    bad = {k: v for k, v in errs.items() if v > QTOL}
+    assert not bad, bad
+    eq, near, B = G.argmax_agreement(q, qr)
+    assert eq + near == B, (eq, near, B)
+    assert bn < 2e-3
 
 
 def test_full_size_properties_b128():
