@@ -306,6 +306,8 @@ static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Sp
     if (backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
         UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
         ep.terms = c->terms;
+        // the wgrad scratch is idle whenever a forward conv / dgrad runs: lend it to the split-K path of small problems
+        umma_set_splitk_scratch(out == c->wscratch ? nullptr : c->wscratch, umma_wgrad_scratch_floats());
         return k_conv_umma(a, w, N, ntaps, out, ep, s);
     }
     return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, s);

@@ -281,7 +281,7 @@ template <int BN, int FL, int TERMS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
-                 int N, int ntaps, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
+                 int N, int ntaps, int m_tiles, int n_tiles, int nz, float* __restrict__ out, ConvEpilogue ep) {
     using Cfg = ConvCfg<BN, TERMS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -298,8 +298,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int BK = Cfg::BK;
     const int kchunks = K / BK;
-    const int iters = ntaps * kchunks;
-    const int total_tiles = m_tiles * n_tiles;
+    // nz > 1: split-K over the taps for small problems (batch-1 inference: 5 m-tiles) -- work item = (tile, z), z owns
+    // taps [z*ntaps/nz, (z+1)*ntaps/nz) and writes a raw partial to out + z*rows*N; a second kernel sums the partials
+    // and applies the epilogue (k_conv_umma).  nz == 1: one work item per tile, all taps.
+    const int taps_per_z = ntaps / nz;
+    const int iters = taps_per_z * kchunks;
+    const int total_tiles = m_tiles * n_tiles * nz;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -317,11 +321,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+                const int tile = work / nz, z = work - tile * nz;
                 const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
                 const int m0 = m_t * UM_BM;
                 for (int it = 0; it < iters; ++it) {
-                    const int t = it / kchunks, kc = it - t * kchunks;
+                    const int tl = it / kchunks, kc = it - tl * kchunks, t = z * taps_per_z + tl;
                     const int off = ntaps == 9 ? (t / 3 - 1) * PITCH + (t % 3 - 1) : 0;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
@@ -342,7 +347,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
                 mbar_wait(tempty_bar(acc), aph ^ 1u);           // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -374,12 +379,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     } else {
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
         int acc = 0; uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+            const int tile = work / nz, z = work - tile * nz;
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
-            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N, out, ep,
-                                         quad, lane);
+            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N,
+                                         out + (size_t)z * rows * N, ep, quad, lane);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     }
@@ -840,6 +846,44 @@ int k_wgrad_reduce(const float* partial, int Cout, int Cin, int ntaps, int nspli
     return 0;
 }
 
+// split-K tail: out = epilogue(sum_z partial[z]) -- the same transforms as epilogue_tile, elementwise
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int nz, int rows, int N, ConvEpilogue ep,
+                                                            float* __restrict__ out) {
+    const int N4 = N >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * N4) return;
+    const int m = (int)(idx / N4), n = (int)(idx - (long long)m * N4) * 4;
+    const size_t o = (size_t)m * N + n, plane = (size_t)rows * N;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(ep.pitch25 && !p25_valid(m % IMG25))) {
+        for (int z = 0; z < nz; ++z) {
+            const float4 p = *reinterpret_cast<const float4*>(partial + z * plane + o);
+            x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+        }
+        if (ep.scale) {
+            const float4 sc = *reinterpret_cast<const float4*>(ep.scale + n), sh = *reinterpret_cast<const float4*>(ep.shift + n);
+            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+        }
+        if (ep.add_prev) { const float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
+        if (ep.res.hi) {
+            float r[4];
+            const uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
+            const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = bf2f(hb[i]) + bf2f(lb[i]);
+            x.x += r[0]; x.y += r[1]; x.z += r[2]; x.w += r[3];
+        }
+        if (ep.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+    }
+    if (out) *reinterpret_cast<float4*>(out + o) = x;
+    if (ep.out_split.hi) {
+        bf16 h[4], l[4];
+        split_store(x.x, h[0], l[0]); split_store(x.y, h[1], l[1]); split_store(x.z, h[2], l[2]); split_store(x.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(ep.out_split.hi + o) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(ep.out_split.lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -871,7 +915,7 @@ static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, i
 static int g_num_sms = 0;
 
 template <int BN, int FL, int TERMS>
-static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s, int nz = 1) {
     using Cfg = ConvCfg<BN, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
     if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -886,11 +930,11 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
         make_map(&mWhi, W.t.hi, W.rows, W.cols, BN, Cfg::BK) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN, Cfg::BK))
         return 1;
     const int m_tiles = ceil_div(A.rows, UM_BM), n_tiles = N / BN;
-    const int grid = m_tiles * n_tiles < g_num_sms ? m_tiles * n_tiles : g_num_sms;
+    const int grid = m_tiles * n_tiles * nz < g_num_sms ? m_tiles * n_tiles * nz : g_num_sms;
     // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
-    conv_umma_kernel<BN, FL, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, out, ep);
+    conv_umma_kernel<BN, FL, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, nz, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
     return 0;
@@ -959,6 +1003,25 @@ int umma_conv_m_tiles(long long rows) { return ceil_div(rows, UM_BM); }
 bool umma_conv_supported(int K, int N) { return K % UM_BK == 0 && (N == 32 || N % 64 == 0); }
 bool umma_wgrad_supported(int Cout, int Cin) { return Cout % 64 == 0 && Cin % 64 == 0; }
 
+// Split-K over the taps (small problems only: the 128 x BN tiles would leave most SMs idle, e.g. 5 m-tiles at batch 1):
+// raw partials of nz tap groups into `scratch`, then one elementwise pass applies the epilogue.
+template <int BN>
+static int conv_splitk(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, int nz, float* scratch,
+                       cudaStream_t s) {
+    ConvEpilogue raw = conv_ep(0);
+    raw.terms = ep.terms;
+    int rc = ep.terms == 1 ? launch_conv<BN, EF_F32, 1>(A, W, N, ntaps, scratch, raw, s, nz) : launch_conv<BN, EF_F32, 3>(A, W, N, ntaps, scratch, raw, s, nz);
+    if (rc) return rc;
+    const long long n = A.rows * (N / 4);
+    splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scratch, nz, (int)A.rows, N, ep, out);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+static float* g_splitk_scratch = nullptr;      // set per call by api.cu (the context's wgrad scratch, idle during forwards)
+static size_t g_splitk_floats = 0;
+void umma_set_splitk_scratch(float* p, size_t floats) { g_splitk_scratch = p; g_splitk_floats = floats; }
+
 int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     if (umma_init()) return 1;
     if (!umma_conv_supported(A.cols, N) || W.cols != A.cols || W.rows != (long long)ntaps * N) {
@@ -966,6 +1029,19 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         return 1;
     }
     if (N == 32) return dispatch_conv<32>(A, W, N, ntaps, out, ep, s);
+    if (ntaps == 9 && !ep.stats && !ep.bn_raw && !ep.add_g && g_splitk_scratch) {
+        if (!g_num_sms) {
+            int dev = 0;
+            SIMQ_CUDA(cudaGetDevice(&dev));
+            SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int bn = N % 128 == 0 ? 128 : 64;
+        const long long tiles = (long long)ceil_div(A.rows, 128) * (N / bn);
+        const int nz = tiles * 9 <= 2 * g_num_sms ? 9 : tiles * 3 <= g_num_sms ? 3 : 1;
+        if (nz > 1 && (size_t)nz * A.rows * N <= g_splitk_floats)
+            return bn == 128 ? conv_splitk<128>(A, W, N, ntaps, out, ep, nz, g_splitk_scratch, s)
+                             : conv_splitk<64>(A, W, N, ntaps, out, ep, nz, g_splitk_scratch, s);
+    }
     // tile policy for N % 256 == 0: the CTA-pair kernel (256 x 256 per pair) runs ~12 % more tensor work per cycle
     // than 128 x 128 single-CTA tiles but quantises worse on small problems; pick the cheaper estimate in units
     // of one 128 x 128 tile time.  SIMQ_CONV_TILE = 128 | 256 | pair overrides (experiments).

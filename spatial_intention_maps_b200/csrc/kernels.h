@@ -116,6 +116,7 @@ struct UmmaTensor {          // a split tensor plus its row count / width, enoug
 int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
 int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, int terms, cudaStream_t s);
 int umma_init();             // resolves cuTensorMapEncodeTiled
+void umma_set_splitk_scratch(float* p, size_t floats);   // scratch for the split-K path of small convs (NULL disables it)
 bool umma_conv_supported(int K, int N);
 int umma_conv_m_tiles(long long rows);     // rows of ConvEpilogue::stats written by k_conv_umma
 bool umma_wgrad_supported(int Cout, int Cin);

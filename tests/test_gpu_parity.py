@@ -312,7 +312,7 @@ def test_full_size_properties_b128():
         q = net(x)
         q_sub = net(x[5:9])
         act, _ = net.greedy_action(x)
-    assert G.relerr(q_sub, q[5:9]) < 1e-6
+    assert G.relerr(q_sub, q[5:9]) < 1e-4      # not bitwise: small batches take the split-K path (different summation order)
     assert torch.equal(act, q.view(128, -1).argmax(1))
     tgt = networks.FCN(5, 1, max_batch=128)
     tgt.load_state_dict(st)
