@@ -234,27 +234,34 @@ def run_simq(args):
 
     # ---- informational: opt-in bf16 mode (1 MMA per product; does NOT meet the parity bar, never the headline) ----
     fast = None
-    if not args.no_fast:
-        pol.eval()
-        with torch.no_grad():
-            q_par = pol(x[:8])
-            pol.set_precision('bf16')
-            q_b16 = pol(x[:8])
-        pol.train()
-        for _ in range(3):
-            step_device()
-        ms_fast = timed(step_device, args.steps)
-        L.simq_profile(1, None, None, None)
-        timed(step_device, max(2, args.steps // 4))
-        fm, ff, fl_ = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
-        L.simq_profile(0, fm, ff, fl_)
-        pol.set_precision('parity')
-        qerr = float((q_b16 - q_par).abs().max() / q_par.abs().max())
-        agree = float((q_b16.view(8, -1).argmax(1) == q_par.view(8, -1).argmax(1)).float().mean())
-        fast = {'value': world * B * args.steps / (ms_fast * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fast / args.steps,
-                'conv_tflops_algorithmic': (ff[0] / (fm[0] * 1e-3)) / 1e12 if fm[0] > 0 else None,
-                'qmap_maxnorm_err_vs_parity_mode': qerr, 'argmax_agreement_vs_parity_mode': agree,
-                'note': 'simq_set_precision(BF16): hi planes only, one tcgen05 MMA per product; fails the 1e-3 parity bar -> not the headline'}
+    if not args.no_fast and world == 1:          # single-GPU only: informational, must never endanger the multi-rank line
+        try:
+            pol.eval()
+            with torch.no_grad():
+                q_par = pol(x[:8])
+                pol.set_precision('bf16')
+                q_b16 = pol(x[:8])
+            pol.train()
+            for _ in range(3):
+                step_device()
+            ms_fast = timed(step_device, args.steps)
+            L.simq_profile(1, None, None, None)
+            timed(step_device, max(2, args.steps // 4))
+            fm, ff, fl_ = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+            L.simq_profile(0, fm, ff, fl_)
+            pol.set_precision('parity')
+            qerr = float((q_b16 - q_par).abs().max() / q_par.abs().max())
+            agree = float((q_b16.view(8, -1).argmax(1) == q_par.view(8, -1).argmax(1)).float().mean())
+            fast = {'value': world * B * args.steps / (ms_fast * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fast / args.steps,
+                    'conv_tflops_algorithmic': (ff[0] / (fm[0] * 1e-3)) / 1e12 if fm[0] > 0 else None,
+                    'qmap_maxnorm_err_vs_parity_mode': qerr, 'argmax_agreement_vs_parity_mode': agree,
+                    'note': 'simq_set_precision(BF16): hi planes only, one tcgen05 MMA per product; fails the 1e-3 parity bar -> not the headline'}
+        except Exception as e:  # noqa: BLE001
+            fast = {'error': f'{type(e).__name__}: {e}'}
+            try:
+                pol.set_precision('parity')
+            except Exception:  # noqa: BLE001
+                pass
 
     if rank == 0:
         sustained, burst, hbm, how = peaks()
