@@ -303,9 +303,12 @@ def run_simq(args):
             'clocks': clocks, 'loss': loss, 'bf16_fast_mode': fast,
         }
         if world == 1 and not args.no_cpu:
-            v, per, cores = cpu_steps(3, 1)
-            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': f'3 timed + 1 warm-up steps of batch {CPU_SAMPLE_B} of the same step (oracle port of train.train, torch CPU fp32)'}
+            try:
+                v, per, cores = cpu_steps(3, 1)
+                line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                        'sample': f'3 timed + 1 warm-up steps of batch {CPU_SAMPLE_B} of the same step (oracle port of train.train, torch CPU fp32)'}
+            except Exception as e:  # noqa: BLE001
+                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {type(e).__name__}: {e}'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

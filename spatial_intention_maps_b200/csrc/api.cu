@@ -127,6 +127,7 @@ struct ActSet {
 struct PackedSet {                   // split-bf16 shadows of the conv weights of one parameter vector
     Split fwd[21], bwd[21];          // 16 3x3 + 3 downsample + head conv1 + head conv2, in network order
     Split stem;                      // resnet18.conv1 as [64][Kp]
+    PackEntry* table; int n_table; long long table_total;     // device table for the one-launch packing kernel
     const float* key; uint64_t version; bool used;
 };
 
@@ -139,6 +140,7 @@ struct simq_ctx {
     PackedSet packed[2]; int packed_next;
     // scratch
     float* partials; float* sums; double* dpartials;
+    BnEntry* bn_table;               // device table of the 22 BatchNorms (one-launch eval affine)
     float *G[2], *g_mid, *du1, *dt, *dz0, *dy0, *hp, *wscratch, *stem_partials;
     Split dyA, dyB, dy2h, dy0s; float* stem_tmp;
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
@@ -210,6 +212,7 @@ static void carve_all(simq_ctx* c, bool dry) {
             c->packed[p].bwd[i] = carve_split(c, n, dry);
         }
         c->packed[p].stem = carve_split(c, (size_t)64 * stem_kp(d.C), dry);
+        c->packed[p].table = carve<PackEntry>(c, 32, dry);
         c->packed[p].key = nullptr; c->packed[p].version = 0; c->packed[p].used = false;
     }
     c->packed_next = 0;
@@ -219,6 +222,7 @@ static void carve_all(simq_ctx* c, bool dry) {
     }
     c->sums = carve<float>(c, 3 * MAX_CH, dry);
     c->dpartials = carve<double>(c, 1024, dry);
+    c->bn_table = carve<BnEntry>(c, 32, dry);
     c->G[0] = carve<float>(c, R25 * 512, dry);
     c->G[1] = carve<float>(c, R25 * 512, dry);
     c->g_mid = carve<float>(c, R25 * 512, dry);
@@ -263,6 +267,35 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     carve_all(c, false);
     e = cudaMemset(c->pool, 0, c->pool_bytes);
     if (e != cudaSuccess) { simq_set_error("simq_ctx_create: memset -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
+    {   // device table of the BatchNorms, in BN-ordinal order
+        const NetDesc& d = c->d;
+        std::vector<BnEntry> host(SIMQ_N_BN);
+        auto put = [&](const BnP& b, int bias_param) {
+            BnEntry& E = host[b.idx];
+            E.gamma_off = d.poff[b.gamma]; E.bias_off = bias_param >= 0 ? d.poff[bias_param] : -1; E.bn_off = d.bnoff[b.idx]; E.ch = b.ch; E.idx = b.idx;
+        };
+        put(d.stem_bn, -1);
+        for (int b = 0; b < 8; ++b) { put(d.blk[b].b1, -1); put(d.blk[b].b2, -1); if (d.blk[b].has_ds) put(d.blk[b].bds, -1); }
+        put(d.hbn1, d.h1_bias); put(d.hbn2, d.h2_bias);
+        e = cudaMemcpy(c->bn_table, host.data(), sizeof(BnEntry) * host.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { simq_set_error("simq_ctx_create: table upload -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
+    }
+    {   // device tables of the one-launch weight packing
+        std::vector<ConvP> convs; conv_list(c->d, convs);
+        for (int p = 0; p < 2; ++p) {
+            std::vector<PackEntry> host(convs.size());
+            long long start = 0;
+            for (size_t i = 0; i < convs.size(); ++i) {
+                PackEntry& E = host[i];
+                E.start = start; E.w_off = c->d.poff[convs[i].w]; E.cout = convs[i].cout; E.cin = convs[i].cin; E.kk = convs[i].k * convs[i].k; E.pad = 0;
+                E.fhi = c->packed[p].fwd[i].hi; E.flo = c->packed[p].fwd[i].lo; E.bhi = c->packed[p].bwd[i].hi; E.blo = c->packed[p].bwd[i].lo;
+                start += (long long)E.cout * E.cin * E.kk;
+            }
+            c->packed[p].n_table = (int)convs.size(); c->packed[p].table_total = start;
+            e = cudaMemcpy(c->packed[p].table, host.data(), sizeof(PackEntry) * host.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { simq_set_error("simq_ctx_create: table upload -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
+        }
+    }
     c->launches0 = g_simq_launches;
     c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0; c->graph_misses = 0;
     if (umma_init()) { cudaFree(c->pool); delete c; return 1; }
@@ -328,11 +361,7 @@ static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version,
         if (c->packed[i].used && c->packed[i].key == params) ps = &c->packed[i];
     if (ps && version != 0 && ps->version == version) return ps;
     if (!ps) { ps = &c->packed[c->packed_next]; c->packed_next ^= 1; ++c->pack_epoch; }
-    std::vector<ConvP> convs; conv_list(c->d, convs);
-    for (size_t i = 0; i < convs.size(); ++i) {
-        if (k_pack_weights(params + c->d.poff[convs[i].w], convs[i].cout, convs[i].cin, convs[i].k * convs[i].k, ps->fwd[i],
-                           ps->bwd[i], s)) { *err = 1; return nullptr; }
-    }
+    if (k_pack_all(params, ps->table, ps->n_table, ps->table_total, s)) { *err = 1; return nullptr; }
     if (k_pack_stem(params + c->d.poff[c->d.stem.w], c->d.C, stem_kp(c->d.C), ps->stem, s)) { *err = 1; return nullptr; }
     ps->key = params; ps->version = version; ps->used = true;
     return ps;
@@ -355,9 +384,9 @@ static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, lo
         TRY(k_bn_finalize_train(c->partials, nparts, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
                                 bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), bnstat(S, b.idx, BS_SCALE),
                                 bnstat(S, b.idx, BS_SHIFT), s));
-    } else {
-        TRY(k_bn_eval_affine(b.ch, gamma, beta, bias, rmean, rvar, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT), s));
     }
+    // eval mode: run_forward has already filled scale/shift of every BN in one launch (k_bn_eval_affine_all)
+    (void)beta; (void)bias; (void)rvar;
     return 0;
 }
 
@@ -380,6 +409,7 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
     const int be = c->backend;
     S.valid = false;
+    if (!training) TRY(k_bn_eval_affine_all(params, bn, c->bn_table, SIMQ_N_BN, S.bnstat, s));   // running-stat BN = per-channel affine
     // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
     if (be == SIMQ_BACKEND_UMMA) {
         if (!reuse_acol) TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));     // else: same input as the previous pass on S
@@ -393,13 +423,7 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     Split in = S.a0;
     Split none{nullptr, nullptr};
     const bool fused_eval = !training && be == SIMQ_BACKEND_UMMA;
-    if (fused_eval)                 // eval-mode BN is a per-channel affine known before the conv runs: fold it into the epilogues
-        for (int b = 0; b < 8; ++b) {
-            const BlockP& P = d.blk[b];
-            TRY(bn_prepare(c, S, P.b1, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
-            TRY(bn_prepare(c, S, P.b2, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
-            if (P.has_ds) TRY(bn_prepare(c, S, P.bds, nullptr, 0, 0, params, bn, nbt, -1, 0, 0, s));
-        }
+    // (eval-mode BN is a per-channel affine known before the conv runs: it is folded into the conv epilogues)
     for (int b = 0; b < 8; ++b) {
         const BlockP& P = d.blk[b];
         auto& A = S.blk[b];

@@ -10,6 +10,9 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
 int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
                         const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s);
+// every BatchNorm of the network in one launch (block = one BN): scale/shift into bnstat[(idx*4 + 2|3) * MAX_CH]
+struct BnEntry { long long gamma_off, bias_off /* -1: none */, bn_off; int ch, idx; };
+int k_bn_eval_affine_all(const float* params, const float* bn, const BnEntry* table_dev, int n, float* bnstat, cudaStream_t s);
 int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rmean,
                      const float* rvar, float* scale, float* shift, cudaStream_t s);
 // out = relu(raw*scale+shift + residual), residual: res_mode 0 none, 1 split tensor, 2 rawd*scaled+shiftd
@@ -36,6 +39,9 @@ int k_sgd_step(float* params, float* grads, float* momentum, long long n, float 
 // ---- weight packing: OIHW fp32 -> split bf16 [tap][n][k] ----
 // fwd: n = cout, k = cin.   bwd (dgrad): n = cin, k = cout, taps flipped.
 int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split bwd, cudaStream_t s);
+// all convs of a network in ONE launch: table entry = one conv (elements [start, start + cout*cin*kk) of the launch)
+struct PackEntry { long long start; long long w_off; int cout, cin, kk, pad; bf16 *fhi, *flo, *bhi, *blo; };
+int k_pack_all(const float* params, const PackEntry* table_dev, int n, long long total, cudaStream_t s);
 
 // ---- backward elementwise ----
 int k_up2_adj(const float* dq, int B, int A, float* dt, cudaStream_t s);

@@ -119,6 +119,29 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
     shift[c] = beta[c] + (bias - rmean[c]) * sc;
 }
 
+__global__ void bn_eval_affine_all_kernel(const float* __restrict__ params, const float* __restrict__ bn, const BnEntry* __restrict__ table,
+                                          float* __restrict__ bnstat) {
+    const BnEntry E = table[blockIdx.x];
+    const float* gamma = params + E.gamma_off;
+    const float* beta = gamma + E.ch;
+    const float* rmean = bn + E.bn_off;
+    const float* rvar = rmean + E.ch;
+    float* scale = bnstat + ((size_t)E.idx * 4 + 2) * MAX_CH;
+    float* shift = bnstat + ((size_t)E.idx * 4 + 3) * MAX_CH;
+    for (int c = threadIdx.x; c < E.ch; c += blockDim.x) {
+        float is = 1.0f / sqrtf(rvar[c] + (float)BN_EPS);
+        float sc = gamma[c] * is;
+        float bias = E.bias_off >= 0 ? params[E.bias_off + c] : 0.f;
+        scale[c] = sc;
+        shift[c] = beta[c] + (bias - rmean[c]) * sc;
+    }
+}
+int k_bn_eval_affine_all(const float* params, const float* bn, const BnEntry* table_dev, int n, float* bnstat, cudaStream_t s) {
+    bn_eval_affine_all_kernel<<<n, 128, 0, s>>>(params, bn, table_dev, bnstat);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rmean,
                      const float* rvar, float* scale, float* shift, cudaStream_t s) {
     bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, s>>>(C, gamma, beta, conv_bias, rmean, rvar, scale, shift);
@@ -546,6 +569,39 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split bwd, cudaStream_t s) {
     long long n = (long long)kk * cout * cin;
     pack_weights_kernel<<<grid_for(n, 256), 256, 0, s>>>(w, cout, cin, kk, fwd, bwd);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+#define PACK_MAX 32
+__global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ params, const PackEntry* __restrict__ table, int n,
+                                                       long long total) {
+    __shared__ PackEntry tb[PACK_MAX];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tb[i] = table[i];
+    __syncthreads();
+    const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= total) return;
+    int e = 0;
+    while (e + 1 < n && gidx >= tb[e + 1].start) ++e;
+    const PackEntry& E = tb[e];
+    const long long idx = gidx - E.start;
+    const float* w = params + E.w_off;
+    const int cin = E.cin, cout = E.cout, kk = E.kk;
+    {   // forward pack: [t][co][ci]
+        int ci = (int)(idx % cin), co = (int)((idx / cin) % cout), t = (int)(idx / ((long long)cin * cout));
+        float v = w[((size_t)co * cin + ci) * kk + t];
+        split_store(v, E.fhi[idx], E.flo[idx]);
+    }
+    {   // dgrad pack: [t][ci][co] with the taps rotated by 180 degrees
+        int co = (int)(idx % cout), ci = (int)((idx / cout) % cin), t = (int)(idx / ((long long)cin * cout));
+        float v = w[((size_t)co * cin + ci) * kk + (kk - 1 - t)];
+        split_store(v, E.bhi[idx], E.blo[idx]);
+    }
+}
+
+int k_pack_all(const float* params, const PackEntry* table_dev, int n, long long total, cudaStream_t s) {
+    if (n > PACK_MAX) { simq_set_error("k_pack_all: %d entries > %d", n, PACK_MAX); return 1; }
+    pack_all_kernel<<<grid_for(total, 256), 256, 0, s>>>(params, table_dev, n, total);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
