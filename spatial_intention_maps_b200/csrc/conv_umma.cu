@@ -130,8 +130,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 #define EPI_LD 36               // floats per staged row (32 + 4 pad: conflict-free float4 row writes and column reads)
 
-// BK = 64: 128-byte K rows, SWIZZLE_128B.  BK = 32: 64-byte K rows, SWIZZLE_64B -- used with BN = 256, where a
-// 64-wide stage would be 96 KB and only two would fit: four 48 KB stages hide the TMA latency better.
+// BK = 64: 128-byte K rows, SWIZZLE_128B.  (A BK = 32 / SWIZZLE_64B variant and a single-CTA 128 x 256 tile were measured
+// and dropped: no gain over these tiles; large-N layers use the CTA-pair kernel instead.)
 // TERMS = 3: split-bf16 operands, lo*hi + hi*lo + hi*hi (parity mode).  TERMS = 1: hi planes only, one MMA per
 // product (plain bf16 "fast" mode: ~3x less tensor work, fails the 1e-3 Q-map bar -- opt-in, see simq_set_precision).
 template <int BN, int TERMS = 3>
@@ -1044,11 +1044,11 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
     }
     // tile policy for N % 256 == 0: the CTA-pair kernel (256 x 256 per pair) runs ~12 % more tensor work per cycle
     // than 128 x 128 single-CTA tiles but quantises worse on small problems; pick the cheaper estimate in units
-    // of one 128 x 128 tile time.  SIMQ_CONV_TILE = 128 | 256 | pair overrides (experiments).
+    // of one 128 x 128 tile time.  SIMQ_CONV_TILE = 128 | pair overrides (experiments).
     static int policy = -1;
     if (policy < 0) {
         const char* e = getenv("SIMQ_CONV_TILE");
-        policy = !e ? 0 : !strcmp(e, "128") ? 1 : !strcmp(e, "256") ? 2 : !strcmp(e, "pair") ? 3 : 0;
+        policy = !e ? 0 : !strcmp(e, "128") ? 1 : !strcmp(e, "pair") ? 3 : 0;
     }
     if (N % 256 == 0 && policy != 1) {
         if (!g_num_sms) {
@@ -1060,7 +1060,6 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         const double cost_single = (double)((t128 + g_num_sms - 1) / g_num_sms);
         const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
         if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, true>(A, W, N, ntaps, out, ep, s);
-        if (policy == 2) return dispatch_conv<256>(A, W, N, ntaps, out, ep, s);
     }
     if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
     return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
