@@ -1,8 +1,18 @@
-"""Drop-in for the reference's ``policies.DQNPolicy`` / ``DQNIntentionPolicy`` (policies.py:11-146):
-same constructor, ``build_policy_nets`` / ``apply_transform`` / ``step`` surface and attributes
-(``policy_nets``, ``intention_nets``, ``device``, ``num_robot_groups``), with the networks computed by
-the simq CUDA library (``networks.FCN``).  One process drives one GPU; the ``DataParallel`` wrapper of
-policies.py:39 is replaced by a non-replicating wrapper that keeps the ``module.`` checkpoint prefix.
+"""Host-side mirror of the reference's policy objects (``policies.DQNPolicy`` policies.py:11-74,
+``policies.DQNIntentionPolicy`` policies.py:76-146) on top of the simq CUDA library.
+
+What the callers of the reference use -- and what is kept: ``DQNPolicy(cfg, train=False, random_seed=None)``;
+attributes ``policy_nets`` / ``intention_nets`` (one network per robot group, ``state_dict`` keys prefixed
+``module.``), ``device``, ``num_robot_groups``, ``robot_group_types``, ``train``; methods
+``build_policy_nets()`` (also used by ``train.py:213`` to create the target nets), ``apply_transform(s)``,
+``step(state, exploration_eps=None, debug=False)``, ``build_intention_nets()``, ``step_intention(state, debug)``.
+``state`` is the environment's nested list ``[[ndarray | None per robot] per group]``; results have the
+same nesting.  The Python ``random`` stream is consumed exactly as by the reference (one ``random()`` per
+pending robot, plus one ``randrange`` when exploring), so seeded rollouts pick the same exploratory actions.
+
+Differences by design: one process drives one GPU (no ``DataParallel`` replication; the wrapper only keeps
+the checkpoint prefix); the greedy action is computed on the device and only its index comes back -- the
+Q-map is copied to the host on ``debug=True`` only (the reference copies it on every step, policies.py:66).
 """
 from __future__ import annotations
 
@@ -13,174 +23,157 @@ import torch
 
 from . import networks
 
+_ACTION_CHANNELS = {'pushing_robot': 1}          # envs.py:810; every other robot type has 2 (envs.py:1090)
+_MAP = 96                                        # envs.py:2010
+
 
 class _StaticEnv:
-    """The three static methods of envs.VectorEnv the policy needs (envs.py:366-376; action-channel
-    counts from envs.py:810 (pushing: 1) and :1090 (lifting / throwing / rescue: 2))."""
+    """Static facts about the environment the policy needs (envs.py:366-376) without importing pybullet."""
 
     @staticmethod
     def get_num_output_channels(robot_type):
-        return 1 if robot_type == 'pushing_robot' else 2
+        return _ACTION_CHANNELS.get(robot_type, 2)
 
     @staticmethod
     def get_action_space(robot_type):
-        return _StaticEnv.get_num_output_channels(robot_type) * 96 * 96
+        return _StaticEnv.get_num_output_channels(robot_type) * _MAP * _MAP
 
     @staticmethod
     def get_state_width():
-        return 96
+        return _MAP
 
 
-try:                                    # inside the reference tree the real class is importable
-    from envs import VectorEnv          # type: ignore
-except Exception:                       # pybullet & co. absent: fall back to the static table
+try:                                             # inside the reference tree the real class is importable
+    from envs import VectorEnv                   # type: ignore
+except Exception:                                # pybullet & co. absent
     VectorEnv = _StaticEnv
+
+
+def _pending(state):
+    """(group index, robot index, state array) for every robot that awaits an action."""
+    for gi, group in enumerate(state):
+        for ri, s in enumerate(group):
+            if s is not None:
+                yield gi, ri, s
+
+
+def _like(state):
+    return [[None] * len(group) for group in state]
 
 
 class DQNPolicy:
     def __init__(self, cfg, train=False, random_seed=None, device=None, max_batch=None):
-        self.cfg = cfg
-        self.robot_group_types = [next(iter(g.keys())) for g in self.cfg.robot_config]
-        self.train = train
+        self.cfg, self.train = cfg, train
         if random_seed is not None:
             random.seed(random_seed)
+        self.robot_group_types = [next(iter(group)) for group in cfg.robot_config]
         self.num_robot_groups = len(self.robot_group_types)
-        if device is None:
-            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
-        self.device = torch.device(device)
-        self.max_batch = max_batch if max_batch is not None else int(getattr(cfg, 'batch_size', networks.DEFAULT_MAX_BATCH))
+        self.device = self._pick_device(device)
+        self.max_batch = int(max_batch if max_batch is not None else getattr(cfg, 'batch_size', networks.DEFAULT_MAX_BATCH))
         self.policy_nets = self.build_policy_nets()
+        self.policy_checkpoint = None
+        if getattr(cfg, 'checkpoint_path', None) is not None:       # resume / evaluate a trained policy
+            self.policy_checkpoint = torch.load(cfg.policy_path, map_location=self.device)
+            self._restore(self.policy_nets, 'state_dicts')
+            print("=> loaded policy '{}'".format(cfg.policy_path))
 
-        if getattr(self.cfg, 'checkpoint_path', None) is not None:          # policies.py:25-33
-            self.policy_checkpoint = torch.load(self.cfg.policy_path, map_location=self.device)
-            for i in range(self.num_robot_groups):
-                self.policy_nets[i].load_state_dict(self.policy_checkpoint['state_dicts'][i])
-                if self.train:
-                    self.policy_nets[i].train()
-                else:
-                    self.policy_nets[i].eval()
-            print("=> loaded policy '{}'".format(self.cfg.policy_path))
+    @staticmethod
+    def _pick_device(device):
+        if device is not None:
+            return torch.device(device)
+        if torch.cuda.is_available():
+            return torch.device('cuda', torch.cuda.current_device())
+        return torch.device('cpu')
+
+    def _restore(self, nets, key):
+        for net, sd in zip(nets, self.policy_checkpoint[key]):
+            net.load_state_dict(sd)
+            net.train(self.train)
+
+    def _new_net(self, c_in, c_out):
+        net = networks.FCN(num_input_channels=c_in, num_output_channels=c_out, max_batch=self.max_batch)
+        return networks.SingleDeviceParallel(net).to(self.device)
 
     def build_policy_nets(self):
-        policy_nets = []
-        for robot_type in self.robot_group_types:
-            num_output_channels = VectorEnv.get_num_output_channels(robot_type)
-            policy_nets.append(networks.SingleDeviceParallel(
-                networks.FCN(num_input_channels=self.cfg.num_input_channels, num_output_channels=num_output_channels,
-                             max_batch=self.max_batch)
-            ).to(self.device))
-        return policy_nets
+        return [self._new_net(self.cfg.num_input_channels, VectorEnv.get_num_output_channels(t)) for t in self.robot_group_types]
 
     def apply_transform(self, s):
-        """torchvision ``ToTensor`` on a float32 HWC ndarray (policies.py:20,44-45): HWC -> CHW, no
-        rescaling, plus a leading batch dimension."""
-        if s.ndim == 2:
-            s = s[:, :, None]
-        return torch.from_numpy(np.ascontiguousarray(s.transpose(2, 0, 1))).unsqueeze(0)
+        """What torchvision's ``ToTensor`` does to a float32 HWC array (policies.py:20, 44-45): HWC -> CHW without
+        rescaling, plus a leading batch axis."""
+        a = np.asarray(s)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        return torch.from_numpy(np.ascontiguousarray(np.moveaxis(a, 2, 0))).unsqueeze(0)
 
-    def _to_device_nhwc(self, s):
-        """(96,96,C) float32 ndarray -> (1,C,96,96) channels_last device tensor (no transpose pass)."""
-        t = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32)).unsqueeze(0)     # (1,96,96,C)
-        return t.to(self.device, non_blocking=True).permute(0, 3, 1, 2)
+    def _act(self, gi, s, eps, want_q):
+        """One robot: epsilon-greedy over the flat (A*96*96) action space; returns (action, Q-map or None)."""
+        fcn = self.policy_nets[gi].module
+        if random.random() < eps:
+            action = random.randrange(VectorEnv.get_action_space(self.robot_group_types[gi]))
+            return action, (fcn.greedy_action_hwc(s, want_q=True)[1] if want_q else None)
+        return fcn.greedy_action_hwc(s, want_q=want_q)
 
     def step(self, state, exploration_eps=None, debug=False):
-        if exploration_eps is None:
-            exploration_eps = self.cfg.final_exploration
-
-        action = [[None for _ in g] for g in state]
-        output = [[None for _ in g] for g in state]
+        eps = self.cfg.final_exploration if exploration_eps is None else exploration_eps
+        action, output = _like(state), _like(state)
+        touched = set()
         with torch.no_grad():
-            for i, g in enumerate(state):
-                robot_type = self.robot_group_types[i]
-                net = self.policy_nets[i]
-                net.eval()
-                for j, s in enumerate(g):
-                    if s is not None:
-                        explore = random.random() < exploration_eps        # same RNG consumption order as policies.py:61-62
-                        if explore:
-                            a = random.randrange(VectorEnv.get_action_space(robot_type))
-                            q = net.module.greedy_action_hwc(s, want_q=True)[1] if debug else None
-                        else:
-                            a, q = net.module.greedy_action_hwc(s, want_q=debug)
-                        action[i][j] = a
-                        if debug:                       # the reference copies the Q-map to the host every step
-                            output[i][j] = q            # (policies.py:66); only done on request here
-                if self.train:
-                    net.train()
-
-        if debug:
-            info = {'output': output}
-            return action, info
-
-        return action
+            for gi, ri, s in _pending(state):
+                if gi not in touched:
+                    self.policy_nets[gi].eval()                      # inference uses the running BN statistics
+                    touched.add(gi)
+                action[gi][ri], output[gi][ri] = self._act(gi, s, eps, debug)
+        if self.train:
+            for gi in touched:
+                self.policy_nets[gi].train()
+        return (action, {'output': output}) if debug else action
 
 
 class DQNIntentionPolicy(DQNPolicy):
+    """Adds the intention-prediction nets ``FCN(C-1 -> 1)``: their sigmoid output replaces the ground-truth
+    intention channel outside of training rollouts that are allowed to use it."""
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.intention_nets = self.build_intention_nets()
-        if getattr(self.cfg, 'checkpoint_path', None) is not None:
-            for i in range(self.num_robot_groups):
-                self.intention_nets[i].load_state_dict(self.policy_checkpoint['state_dicts_intention'][i])
-                if self.train:
-                    self.intention_nets[i].train()
-                else:
-                    self.intention_nets[i].eval()
+        if self.policy_checkpoint is not None:
+            self._restore(self.intention_nets, 'state_dicts_intention')
             print("=> loaded intention network '{}'".format(self.cfg.policy_path))
 
     def build_intention_nets(self):
-        intention_nets = []
-        for _ in range(self.num_robot_groups):
-            intention_nets.append(networks.SingleDeviceParallel(
-                networks.FCN(num_input_channels=(self.cfg.num_input_channels - 1), num_output_channels=1,
-                             max_batch=self.max_batch)
-            ).to(self.device))
-        return intention_nets
+        return [self._new_net(self.cfg.num_input_channels - 1, 1) for _ in self.robot_group_types]
+
+    def _predict(self, gi, s):
+        x = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32)).unsqueeze(0).to(self.device).permute(0, 3, 1, 2)
+        return torch.sigmoid(self.intention_nets[gi](x))[0, 0].cpu().numpy()
 
     def step_intention(self, state, debug=False):
-        state_intention = [[None for _ in g] for g in state]
-        output_intention = [[None for _ in g] for g in state]
+        augmented, predicted = _like(state), _like(state)
+        touched = set()
         with torch.no_grad():
-            for i, g in enumerate(state):
-                self.intention_nets[i].eval()
-                for j, s in enumerate(g):
-                    if s is not None:
-                        s_copy = s.copy()
-                        x = self._to_device_nhwc(s)
-                        o = torch.sigmoid(self.intention_nets[i](x)).squeeze(0).squeeze(0).cpu().numpy()
-                        state_intention[i][j] = np.concatenate((s_copy, np.expand_dims(o, 2)), axis=2)
-                        output_intention[i][j] = o
-                if self.train:
-                    self.intention_nets[i].train()
-
-        if debug:
-            info = {'output_intention': output_intention}
-            return state_intention, info
-
-        return state_intention
+            for gi, ri, s in _pending(state):
+                if gi not in touched:
+                    self.intention_nets[gi].eval()
+                    touched.add(gi)
+                p = self._predict(gi, s)
+                predicted[gi][ri] = p
+                augmented[gi][ri] = np.concatenate((s, p[:, :, None]), axis=2)
+        if self.train:
+            for gi in touched:
+                self.intention_nets[gi].train()
+        return (augmented, {'output_intention': predicted}) if debug else augmented
 
     def step(self, state, exploration_eps=None, debug=False, use_ground_truth_intention=False):
-        if self.train and use_ground_truth_intention:
+        if self.train and use_ground_truth_intention:                # the state already carries the true intention map
             return super().step(state, exploration_eps=exploration_eps, debug=debug)
-
-        if self.train:                              # remove the ground-truth intention map
-            state_copy = [[None for _ in g] for g in state]
-            for i, g in enumerate(state):
-                for j, s in enumerate(g):
-                    if s is not None:
-                        state_copy[i][j] = s[:, :, :-1]
-            state = state_copy
-
-        state = self.step_intention(state, debug=debug)
-        if debug:
-            state, info_intention = state
-
-        action = super().step(state, exploration_eps=exploration_eps, debug=debug)
-
-        if debug:
-            action, info = action
-            info['state_intention'] = state
-            info['output_intention'] = info_intention['output_intention']
-            return action, info
-
-        return action
+        if self.train:                                               # drop the ground-truth channel, predict it instead
+            state = [[None if s is None else s[:, :, :-1] for s in group] for group in state]
+        result = self.step_intention(state, debug=debug)
+        state, intention_info = result if debug else (result, None)
+        result = super().step(state, exploration_eps=exploration_eps, debug=debug)
+        if not debug:
+            return result
+        action, info = result
+        info['state_intention'] = state
+        info['output_intention'] = intention_info['output_intention']
+        return action, info
