@@ -300,6 +300,49 @@ def test_forward_full_batch128_matches_oracle():
     assert bn < 2e-3
 
 
+@pytest.mark.parametrize('mode', [0, 1, 2], ids=['fwd', 'dgrad', 'wgrad'])
+def test_pair_kernels_full_size_against_fma_comparator(mode):
+    """B=128, 512 -> 512 3x3 (M = 80000 rows: every CTA pair busy for ~9 rounds; wgrad: 4 row splits of 20000 rows):
+    the tcgen05 CTA-pair kernels against the fp32-FMA comparator kernels on the same split-bf16 operands
+    (independent arithmetic), plus linearity out(a + b) == out(a) + out(b) for the forward conv."""
+    import ctypes as C
+    from spatial_intention_maps_b200 import _lib
+    B, Ci, Co = 128, 512, 512
+    ctx = _lib.Ctx(0, 4, 2, B)
+    g = torch.Generator(device=G.DEV).manual_seed(5 + mode)
+    a = torch.randn(B, Ci, 24, 24, device=G.DEV, generator=g)
+    a2 = torch.randn(B, Co, 24, 24, device=G.DEV, generator=g) if mode == 2 else None
+    w = torch.randn(Co, Ci, 3, 3, device=G.DEV, generator=g) * (2.0 / (Ci * 9)) ** 0.5
+    shape = (Co, Ci, 3, 3) if mode == 2 else (B, Co if mode == 0 else Ci, 24, 24)
+
+    def run(backend, x):
+        out = torch.empty(shape, dtype=torch.float32, device=G.DEV)
+        _lib.check(_lib.lib().simq_test_conv(ctx.handle, backend, mode, B, Ci, Co, 3, _lib.ptr(x), _lib.ptr(a2), _lib.ptr(w), _lib.ptr(out),
+                                             _lib.stream_ptr()), 'simq_test_conv')
+        return out
+    fast, slow = run(_lib.BACKEND_UMMA, a), run(_lib.BACKEND_FMA, a)
+    assert float((fast - slow).abs().max() / slow.abs().max()) < (2e-4 if mode == 2 else 5e-5)
+    if mode == 0:
+        b = torch.randn(B, Ci, 24, 24, device=G.DEV, generator=g)
+        lin = run(_lib.BACKEND_UMMA, a + b) - fast - run(_lib.BACKEND_UMMA, b)
+        assert float(lin.abs().max() / fast.abs().max()) < 1e-4
+    torch.cuda.synchronize()
+    ctx.close()
+
+
+def test_workspace_grows_with_the_batch():
+    """A forward larger than the context's max_batch re-allocates the workspace transparently (same result as
+    a network created for that batch)."""
+    from spatial_intention_maps_b200 import synth
+    small, _ = G.make_net(4, 2, 3, max_batch=2)
+    big, _ = G.make_net(4, 2, 3, max_batch=6)
+    x = torch.from_numpy(synth.synth_states(6, 4, 8)).to(G.DEV).permute(0, 3, 1, 2)
+    small.eval(); big.eval()
+    with torch.no_grad():
+        small(x[:2])
+        assert torch.equal(small(x), big(x)) and small.max_batch >= 6
+
+
 def test_full_size_properties_b128():
     """c3 size (B=128, C=5, A=1): eval forward is per-sample independent (a sample's Q-map does not
     depend on its batch-mates), greedy_action == arg-max of the forward, and a train step is finite,
