@@ -119,6 +119,36 @@ def cpu_steps(steps, warmup, B=CPU_SAMPLE_B):
     return B * len(ts) / total, total / len(ts), cores
 
 
+def torch_gpu_steps(dev, B, steps, warmup, allow_tf32):
+    """The reference's step through stock PyTorch library kernels (cuDNN / ATen) on the SAME GPU: the oracle port of
+    train.train with its tensors on the device.  Informational ("the library path to beat"): it is
+    neither the product path nor the reference arm."""
+    import torch
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import synth
+    from tests.gpu_checks import batch_tensors
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    torch.backends.cudnn.benchmark = True                                   # train.py:23
+    try:
+        pol = {k: v.to(dev) for k, v in O.make_state(C_IN, A_OUT, 0, perturb=False).items()}
+        tgt = {k: v.clone() for k, v in pol.items()}
+        batch = synth.synth_batch(B, C_IN, A_OUT, 1234, terminal_every=TERMINAL_EVERY)
+        tens = [t.to(dev) for t in batch_tensors(batch)]
+        mom = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize(); e0.record()
+            r = O.dqn_step(pol, tgt, mom, *tens, discount=GAMMA)
+            mom = r['momentum']
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -263,6 +293,19 @@ def run_simq(args):
             except Exception:  # noqa: BLE001
                 pass
 
+    # ---- informational: the same step through stock PyTorch library kernels (cuDNN) on this GPU ----
+    torch_gpu = None
+    if not args.no_torch_gpu and world == 1:
+        try:
+            del q_grad
+            torch.cuda.empty_cache()
+            torch_gpu = {'fp32': torch_gpu_steps(dev, B, 5, 2, False), 'tf32': torch_gpu_steps(dev, B, 5, 2, True),
+                         'note': 'oracle port of train.train on cuda tensors (cuDNN / ATen eager kernels, cudnn.benchmark as train.py:23, '
+                                 'incl. two .item() syncs per step); fp32 = allow_tf32 False (the parity-grade setting), tf32 = PyTorch default '
+                                 '(fails the 1e-3 bar in train mode, SURVEY.md 7.2-1)'}
+        except Exception as e:  # noqa: BLE001
+            torch_gpu = {'error': f'{type(e).__name__}: {e}'}
+
     if rank == 0:
         sustained, burst, hbm, how = peaks()
         traffic, traffic_note = None, None
@@ -300,7 +343,7 @@ def run_simq(args):
                                           'ms_per_step_in_kernel': pm[1] / args.steps}},
             'step_tflops_algorithmic': STEP_GFLOP * 1e-3 * value,
             'fwd_bwd_only': {'value': world * B / (ms_fb * 1e-3), 'unit': UNIT, 'ms': ms_fb},
-            'clocks': clocks, 'loss': loss, 'bf16_fast_mode': fast,
+            'clocks': clocks, 'loss': loss, 'bf16_fast_mode': fast, 'torch_cudnn_same_gpu': torch_gpu,
         }
         if world == 1 and not args.no_cpu:
             try:
@@ -323,6 +366,7 @@ def main():
     ap.add_argument('--batch', type=int, default=128, help='per-GPU minibatch')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fast', action='store_true', help='skip the informational bf16-mode measurement')
+    ap.add_argument('--no-torch-gpu', action='store_true', help='skip the informational PyTorch/cuDNN-on-GPU measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -242,8 +242,8 @@ def dqn_step(policy, target, momentum: Optional[Dict[str, torch.Tensor]],
 
     output = forward(work, state, True)                                            # :114
     q_sa = output.view(B, -1).gather(1, action.view(B, 1)).squeeze(1)              # :115
-    next_v = torch.zeros(B, dtype=state.dtype)                                     # :116
-    best = torch.zeros(0, dtype=torch.long)
+    next_v = torch.zeros(B, dtype=state.dtype, device=state.device)                # :116
+    best = torch.zeros(0, dtype=torch.long, device=state.device)
     with torch.no_grad():
         if next_state.shape[0] > 0:
             if double_dqn:                                                         # :119-122
