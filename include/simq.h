@@ -3,7 +3,7 @@
  * The reference (jimmyyhwu/spatial-intention-maps @ 336e03a) has no FFI: its boundary for this path
  * is the Python duck-type surface of networks.FCN / train.train.  Each entry point
  * below replaces one piece of that surface; the Python host side
- * (spatial_intention_maps_b200/{networks,train,policies}.py) binds them with ctypes and mirrors
+ * (spatial_intention_maps_b200/{networks,train,policies,replay}.py) binds them with ctypes and mirrors
  * the reference names.  INTEGRATION.md shows the binding a reference maintainer would add.
  *
  * Conventions: every function returns 0 on success, nonzero on error (message: simq_last_error(),
@@ -91,7 +91,9 @@ int simq_sgd_step(simq_ctx*, float* params, float* grads, float* momentum, float
 /* Replaces the whole of train.train (train.py:108-141) on device-resident inputs: online forward
  * on s (saving), online train-mode forward on s' (argmax), target eval forward on s', tail,
  * backward, clip, SGD.  out2 as in simq_dqn_tail.  apply_update==0 stops after the gradients
- * (data-parallel callers all-reduce `grads`, then call simq_sgd_step).  target_version: as params_version of
+ * (data-parallel callers all-reduce `grads`, then call simq_sgd_step).  From the second call on, the ~290
+ * launches of the step are replayed as ONE CUDA graph per distinct argument tuple (all pointers and scalars are part
+ * of the key; SIMQ_GRAPH=0 in the environment keeps the eager launches; results are bitwise identical).  target_version: as params_version of
  * simq_fcn_forward, for the target network's packed weights (it changes only at target syncs). */
 int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const float* target_params,
                     const float* target_bn, uint64_t target_version, float* grads, float* momentum,
