@@ -149,6 +149,33 @@ def torch_gpu_steps(dev, B, steps, warmup, allow_tf32):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
 
 
+def cstar_steps(dev, B, steps):
+    """The full train step on the north_star's headline shape (SURVEY.md section 8 row c*: C=8, A=2, gamma 0.85, batch B)."""
+    import torch
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    Cs, As = 8, 2
+    pol = networks.FCN(Cs, As, max_batch=B).to(dev).train()
+    tgt = networks.FCN(Cs, As, max_batch=B)
+    tgt.load_state_dict(pol.state_dict())
+    tgt = tgt.to(dev).eval()
+    opt = torch.optim.SGD(pol.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    hb = T.HostBatch(B, Cs).fill(synth.synth_batch(B, Cs, As, 4321, terminal_every=TERMINAL_EVERY))
+    db = T.DeviceBatch(B, Cs, dev).upload(hb)
+    for _ in range(3):
+        T.train_step_device(pol, tgt, opt, db, B, GAMMA, 100, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        T.train_step_device(pol, tgt, opt, db, B, GAMMA, 100, True)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    loss = float(db.out2[0])
+    del pol, tgt, opt, db
+    torch.cuda.empty_cache()
+    return {'workload': f'c* C={Cs} A={As} gamma={GAMMA} batch={B} double-DQN', 'ms_per_step': ms, 'value': B / (ms * 1e-3), 'unit': UNIT,
+            'loss': loss}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -250,6 +277,19 @@ def run_simq(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     loss = float(db.out2_host[0])
+    # ---- informational: the same step under the serial schedule (one stream; simq_set_schedule) ----
+    serial = None
+    if not args.no_serial:
+        pol.set_schedule('serial')
+        for _ in range(3):
+            step_device()
+        ms_serial = timed(step_device, args.steps)
+        pol.set_schedule('lanes')
+        for _ in range(2):
+            step_device()
+        serial = {'ms_per_step': ms_serial / args.steps, 'value': world * B * args.steps / (ms_serial * 1e-3), 'unit': UNIT,
+                  'note': 'simq_set_schedule(SERIAL): every kernel of the step on one stream; the headline uses the default two-lane '
+                          'schedule (forward(s) beside forwards(s\'), weight gradients beside the dgrad chain), bit-identical results'}
     # forward+backward only (the literal BASELINE.json wording), informational
     x = db.s.permute(0, 3, 1, 2)
 
@@ -261,6 +301,20 @@ def run_simq(args):
     q_grad.view(B, -1)[:, 7] = 1.0 / B
     fwd_bwd()
     ms_fb = timed(fwd_bwd, max(2, args.steps // 2)) / max(2, args.steps // 2)
+
+    def fwd_only():
+        with torch.no_grad():
+            pol(x)
+    fwd_only()
+    ms_f = timed(fwd_only, max(2, args.steps // 2)) / max(2, args.steps // 2)
+
+    # ---- informational: the north_star's headline shape c* (C=8 input channels, A=2), same step, same batch ----
+    cstar = None
+    if not args.no_cstar and world == 1:
+        try:
+            cstar = cstar_steps(dev, B, max(2, args.steps // 2))
+        except Exception as e:  # noqa: BLE001
+            cstar = {'error': f'{type(e).__name__}: {e}'}
 
     # ---- informational: opt-in bf16 mode (1 MMA per product; does NOT meet the parity bar, never the headline) ----
     fast = None
@@ -335,6 +389,8 @@ def run_simq(args):
                          'unit': 'TFLOP/s', 'frac': conv_tf / sustained, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': f'{how} bf16 sustained',
                          'launches': int(pl[0]), 'ms_per_step_in_kernel': pm[0] / args.steps,
                          'share_of_step': (pm[0] / args.steps) / (ms_prof / args.steps), 'ms_per_step_profiled_pass': ms_prof / args.steps,
+                         'profiled_pass': 'eager launches, serial schedule (one stream), CUDA events around every tensor-core launch: a '
+                                          'kernel\'s events time that kernel alone; `value` comes from the graphed two-lane pass',
                          'note': 'algorithmic FLOPs (2*valid_pixels*N*K*taps); the kernel issues 3 bf16 MMAs per product over 625/576 padded rows, '
                                  'so issued tensor work = 3.26x algorithmic: issued_frac = frac*3.26',
                          'issued_frac': conv_tf * 3 * 625 / 576 / sustained,
@@ -343,6 +399,8 @@ def run_simq(args):
                                           'ms_per_step_in_kernel': pm[1] / args.steps}},
             'step_tflops_algorithmic': STEP_GFLOP * 1e-3 * value,
             'fwd_bwd_only': {'value': world * B / (ms_fb * 1e-3), 'unit': UNIT, 'ms': ms_fb},
+            'forward_only': {'value': world * B / (ms_f * 1e-3), 'unit': UNIT, 'ms': ms_f, 'note': 'train-mode BN, no_grad'},
+            'serial_schedule': serial, 'c_star': cstar,
             'clocks': clocks, 'loss': loss, 'bf16_fast_mode': fast, 'torch_cudnn_same_gpu': torch_gpu,
         }
         if world == 1 and not args.no_cpu:
@@ -367,6 +425,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fast', action='store_true', help='skip the informational bf16-mode measurement')
     ap.add_argument('--no-torch-gpu', action='store_true', help='skip the informational PyTorch/cuDNN-on-GPU measurement')
+    ap.add_argument('--no-serial', action='store_true', help='skip the informational serial-schedule measurement')
+    ap.add_argument('--no-cstar', action='store_true', help='skip the informational C=8 / A=2 measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -40,6 +40,12 @@ enum { SIMQ_BACKEND_UMMA = 0, SIMQ_BACKEND_FMA = 1 };
  * three MMAs (meets the 1e-3 Q-map / arg-max bar).  BF16: hi planes only, one MMA per product -- ~2.5x faster
  * conv kernels, Q-map error ~1e-2 (FAILS the parity bar; opt-in for users who train in bf16 anyway). */
 enum { SIMQ_PRECISION_PARITY = 0, SIMQ_PRECISION_BF16 = 1 };
+/* how the independent pieces of a step are scheduled.  LANES (default): two streams forked / joined with events -- the
+ * forward on s beside the two forwards on s' (train.py:114 / :121-122), the weight-gradient GEMMs beside the
+ * BatchNorm-backward + dgrad chain (train.py:132) -- so HBM-bound kernels run under tensor-bound ones; inside a
+ * captured step the lanes are two branches of the CUDA graph.  SERIAL: one stream, launch order = reference order.
+ * Both give bit-identical results (no atomics, per-lane scratch).  Env SIMQ_LANES=0 makes SERIAL the default. */
+enum { SIMQ_SCHEDULE_SERIAL = 0, SIMQ_SCHEDULE_LANES = 1 };
 /* x layouts accepted by the stem */
 /* SIMQ_X_NHWC_PLUS1: [B,96,96,C+1] whose last channel is NOT a network input (train.py:145-146) */
 enum { SIMQ_X_NCHW = 0, SIMQ_X_NHWC = 1, SIMQ_X_NHWC_PLUS1 = 2 };
@@ -57,6 +63,7 @@ int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch);
 void simq_ctx_destroy(simq_ctx*);
 int simq_set_backend(simq_ctx*, int backend);
 int simq_set_precision(simq_ctx*, int mode);
+int simq_set_schedule(simq_ctx*, int mode);
 size_t simq_workspace_bytes(const simq_ctx*);
 
 /* Replaces FCN.forward (networks.py:16-26).  x: f32 [B,C,96,96] (NCHW) or [B,96,96,C] (NHWC);

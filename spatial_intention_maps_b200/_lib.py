@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libsimq.so')
 
 BACKEND_UMMA, BACKEND_FMA = 0, 1
 PRECISION_PARITY, PRECISION_BF16 = 0, 1
+SCHEDULE_SERIAL, SCHEDULE_LANES = 0, 1
 X_NCHW, X_NHWC, X_NHWC_PLUS1 = 0, 1, 2
 N_BN = 22
 N_PARAM_TENSORS = 70
@@ -34,6 +35,7 @@ _PROTOS = {
     'simq_ctx_destroy': (None, [_c_ctx]),
     'simq_set_backend': (C.c_int, [_c_ctx, C.c_int]),
     'simq_set_precision': (C.c_int, [_c_ctx, C.c_int]),
+    'simq_set_schedule': (C.c_int, [_c_ctx, C.c_int]),
     'simq_workspace_bytes': (C.c_size_t, [_c_ctx]),
     'simq_fcn_forward': (C.c_int, [_c_ctx, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_uint64, _p]),
     'simq_fcn_backward': (C.c_int, [_c_ctx, _p, _p, C.c_int, _p, C.c_int, _p, _p]),

@@ -143,6 +143,11 @@ struct simq_ctx {
     BnEntry* bn_table;               // device table of the 22 BatchNorms (one-launch eval affine)
     float *G[2], *g_mid, *du1, *dt, *dz0, *dy0, *hp, *wscratch, *stem_partials;
     Split dyA, dyB, dy2h, dy0s; float* stem_tmp;
+    // second lane (see "lanes" below): its own column-sum partials and split-K / wgrad scratch, the ping-pong partner of
+    // dyA, and the stash of the deferred running-statistics update of the s' pass
+    float *partials2, *wscratch2; Split dyA2; double* bn_defer;
+    cudaStream_t aux_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[4];
+    int lanes_mode;                  // -1: read SIMQ_LANES on first use; 0 serial schedule; 1 two lanes
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     long long launches0;
     // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
@@ -220,6 +225,10 @@ static void carve_all(simq_ctx* c, bool dry) {
         size_t need = (size_t)STAT_BLOCKS * 3 * MAX_CH, conv_need = (size_t)umma_conv_m_tiles((long long)R48) * 2 * MAX_CH;
         c->partials = carve<float>(c, need > conv_need ? need : conv_need, dry);
     }
+    {
+        size_t need = (size_t)STAT_BLOCKS * 3 * MAX_CH, conv_need = (size_t)umma_conv_m_tiles((long long)R48) * 2 * MAX_CH;
+        c->partials2 = carve<float>(c, need > conv_need ? need : conv_need, dry);
+    }
     c->sums = carve<float>(c, 3 * MAX_CH, dry);
     c->dpartials = carve<double>(c, 1024, dry);
     c->bn_table = carve<BnEntry>(c, 32, dry);
@@ -232,8 +241,11 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->dy0 = carve<float>(c, R48 * 64, dry);
     c->hp = carve<float>(c, (size_t)STAT_BLOCKS * 6 * 32, dry);
     c->wscratch = carve<float>(c, umma_wgrad_scratch_floats(), dry);
+    c->wscratch2 = carve<float>(c, umma_wgrad_scratch_floats(), dry);
+    c->bn_defer = carve<double>(c, (size_t)SIMQ_N_BN * 2 * MAX_CH, dry);
     c->stem_partials = carve<float>(c, stem_wgrad_partial_floats(d.C), dry);
     c->dyA = carve_split(c, R25 * 512, dry);
+    c->dyA2 = carve_split(c, R25 * 512, dry);
     c->dyB = carve_split(c, R25 * 512, dry);
     c->dy2h = carve_split(c, R48 * 32, dry);
     c->dy0s = carve_split(c, R48 * 64, dry);
@@ -297,6 +309,9 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
         }
     }
     c->launches0 = g_simq_launches;
+    c->aux_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1;
+    for (auto& e : c->ev_pool) e = nullptr;
+    for (auto& e : c->ev_done) e = nullptr;
     c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0; c->graph_misses = 0;
     if (umma_init()) { cudaFree(c->pool); delete c; return 1; }
     *out = c;
@@ -308,6 +323,9 @@ extern "C" void simq_ctx_destroy(simq_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (auto e : c->ev_pool) if (e) cudaEventDestroy(e);
+    for (auto e : c->ev_done) if (e) cudaEventDestroy(e);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     cudaFree(c->pool);
@@ -334,24 +352,81 @@ extern "C" int64_t simq_launch_count(const simq_ctx* c) { return c ? (int64_t)(g
 static inline float* bnstat(ActSet& S, int bn, int which) { return S.bnstat + ((size_t)bn * 4 + which) * MAX_CH; }
 enum { BS_MEAN = 0, BS_INVSTD = 1, BS_SCALE = 2, BS_SHIFT = 3 };
 
+// ------------------------------------------------------------------------------------------------
+// lanes: independent pieces of a step run on two streams (forked / joined with events, so the same code
+// serves eager launches and stream capture, where the fork becomes two branches of the CUDA graph):
+//   forwards : lane A = online pass on s (saved set), lane B = online pass on s' then the target pass (scratch set)
+//   backward : lane A = BatchNorm backward + dgrad chain, lane B = every weight-gradient GEMM
+// so that the HBM-bound elementwise kernels of one lane run under the tensor-bound GEMMs of the other and the
+// tails of the persistent GEMM kernels are filled.  Results are bit-identical to the serial schedule: each lane owns its
+// scratch (column-sum partials, split-K / wgrad scratch), nothing is accumulated atomically, and the one ordered
+// side effect two concurrent passes share -- the BatchNorm running statistics of the online net, updated by the s
+// pass and then by the s' pass (train.py:114, :121) -- is applied for the s' pass after the join from a stash.
+// SIMQ_LANES=0 or simq_set_schedule(ctx, SIMQ_SCHEDULE_SERIAL) selects the serial schedule (also used while
+// per-kernel event profiling is on, so that a kernel's events time that kernel alone).
+// ------------------------------------------------------------------------------------------------
+struct Lane {
+    cudaStream_t s;
+    float* partials;      // per-tile column sums of the conv / dgrad epilogues, colstats / bn_bwd_reduce partials
+    float* scratch;       // split-K partials of small forward convs; wgrad split partials
+    double* defer;        // non-NULL: train-mode BatchNorm stashes its running-statistics update here (see above)
+};
+static Lane main_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials, c->wscratch2, nullptr}; }
+static Lane side_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials2, c->wscratch, nullptr}; }
+
+static bool lanes_enabled(simq_ctx* c) {
+    if (c->lanes_mode < 0) { const char* e = getenv("SIMQ_LANES"); c->lanes_mode = e ? (atoi(e) != 0) : 1; }
+    return c->lanes_mode == 1 && !g_prof_on;
+}
+static int lanes_init(simq_ctx* c) {
+    if (c->aux_stream) return 0;
+    SIMQ_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_pool) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_done) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+// work enqueued on `to` after this call starts after everything enqueued on `from` so far
+static int lane_order(simq_ctx* c, cudaStream_t from, cudaStream_t to, cudaEvent_t ev = nullptr) {
+    if (from == to) return 0;
+    if (!ev) { ev = c->ev_pool[c->ev_next]; c->ev_next = (c->ev_next + 1) % 32; }
+    SIMQ_CUDA(cudaEventRecord(ev, from));
+    SIMQ_CUDA(cudaStreamWaitEvent(to, ev, 0));
+    return 0;
+}
+// the side lane of a call on stream s: a second stream, or s itself under the serial schedule
+static int side_stream_for(simq_ctx* c, cudaStream_t s, cudaStream_t* out) {
+    *out = s;
+    if (!lanes_enabled(c)) return 0;
+    if (lanes_init(c)) return 1;
+    *out = c->aux_stream;
+    return 0;
+}
+
+extern "C" int simq_set_schedule(simq_ctx* c, int mode) {
+    if (!c || (mode != SIMQ_SCHEDULE_SERIAL && mode != SIMQ_SCHEDULE_LANES)) { simq_set_error("simq_set_schedule: bad argument"); return 1; }
+    c->lanes_mode = mode == SIMQ_SCHEDULE_LANES ? 1 : 0;
+    ++c->pack_epoch;                 // invalidates captured graphs (the key carries pack_epoch)
+    return 0;
+}
+
 static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Split W, int N, int ntaps, float* out,
-                    ConvEpilogue ep, cudaStream_t s) {
+                    ConvEpilogue ep, const Lane& L) {
     if (backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
         UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
         ep.terms = c->terms;
-        // the wgrad scratch is idle whenever a forward conv / dgrad runs: lend it to the split-K path of small problems
-        umma_set_splitk_scratch(out == c->wscratch ? nullptr : c->wscratch, umma_wgrad_scratch_floats());
-        return k_conv_umma(a, w, N, ntaps, out, ep, s);
+        // the lane's scratch is idle whenever one of its forward convs / dgrads runs: lend it to the split-K path of small problems
+        umma_set_splitk_scratch(out == L.scratch ? nullptr : L.scratch, umma_wgrad_scratch_floats());
+        return k_conv_umma(a, w, N, ntaps, out, ep, L.s);
     }
-    return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, s);
+    return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, L.s);
 }
 static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW,
-                     cudaStream_t s) {
+                     const Lane& L) {
     if (backend == SIMQ_BACKEND_UMMA && umma_wgrad_supported(Cout, Cin)) {
         UmmaTensor y{dY, rows, Cout}, x{X, rows, Cin};
-        return k_wgrad_umma(y, x, ntaps, dW, c->wscratch, c->terms, s);
+        return k_wgrad_umma(y, x, ntaps, dW, L.scratch, c->terms, L.s);
     }
-    return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, c->wscratch, s);
+    return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, L.scratch, L.s);
 }
 
 static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version, cudaStream_t s, int* err) {
@@ -372,7 +447,8 @@ static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version,
 // BatchNorm forward bookkeeping for one BN: fills mean/invstd/scale/shift of set S.
 // nparts > 0: the conv epilogue already left `nparts` partial rows in c->partials; 0: reduce `raw` here.
 static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, long long rows, double count, const float* params,
-                      float* bn, int64_t* nbt, int bias_param, int training, int nparts, cudaStream_t s) {
+                      float* bn, int64_t* nbt, int bias_param, int training, int nparts, const Lane& L) {
+    cudaStream_t s = L.s;
     const NetDesc& d = c->d;
     const float* gamma = params + d.poff[b.gamma];
     const float* beta = params + d.poff[b.gamma + 1];
@@ -380,8 +456,9 @@ static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, lo
     float* rmean = bn + d.bnoff[b.idx];
     float* rvar = rmean + b.ch;
     if (training) {
-        if (nparts == 0) { TRY(k_colstats(raw, rows, b.ch, c->partials, s)); nparts = STAT_BLOCKS; }
-        TRY(k_bn_finalize_train(c->partials, nparts, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
+        if (nparts == 0) { TRY(k_colstats(raw, rows, b.ch, L.partials, s)); nparts = STAT_BLOCKS; }
+        TRY(k_bn_finalize_train(L.partials, nparts, b.ch, count, gamma, beta, bias, rmean, rvar, nbt ? (long long*)(nbt + b.idx) : nullptr,
+                                L.defer ? L.defer + (size_t)b.idx * 2 * MAX_CH : nullptr,
                                 bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), bnstat(S, b.idx, BS_SCALE),
                                 bnstat(S, b.idx, BS_SHIFT), s));
     }
@@ -394,16 +471,17 @@ static int bn_prepare(simq_ctx* c, ActSet& S, const BnP& b, const float* raw, lo
 // epilogue emits the per-tile column sums itself (no extra pass over the raw output).
 static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Split W, int N, int ntaps, float* raw, int pitch25,
                    const BnP& b, double count, const float* params, float* bn, int64_t* nbt, int bias_param, int training,
-                   cudaStream_t s) {
+                   const Lane& L) {
     ConvEpilogue ep = conv_ep(pitch25);
     int nparts = 0;
-    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = c->partials; nparts = umma_conv_m_tiles(rows); }
-    TRY(conv_any(c, c->backend, in, rows, K, W, N, ntaps, raw, ep, s));
-    return bn_prepare(c, S, b, raw, rows, count, params, bn, nbt, bias_param, training, nparts, s);
+    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = L.partials; nparts = umma_conv_m_tiles(rows); }
+    TRY(conv_any(c, c->backend, in, rows, K, W, N, ntaps, raw, ep, L));
+    return bn_prepare(c, S, b, raw, rows, count, params, bn, nbt, bias_param, training, nparts, L);
 }
 
 static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* bn, int64_t* nbt, const float* x, int B,
-                       int x_layout, int training, ActSet& S, float* q, cudaStream_t s, bool reuse_acol = false) {
+                       int x_layout, int training, ActSet& S, float* q, const Lane& L, bool reuse_acol = false) {
+    cudaStream_t s = L.s;
     const NetDesc& d = c->d;
     const long long R25 = (long long)B * IMG25, R48 = (long long)B * 2304;
     const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
@@ -413,10 +491,10 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
     if (be == SIMQ_BACKEND_UMMA) {
         if (!reuse_acol) TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));     // else: same input as the previous pass on S
-        TRY(conv_bn(c, S, S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, s));
+        TRY(conv_bn(c, S, S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, L));
     } else {
         TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
-        TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, 0, s));
+        TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, 0, L));
     }
     TRY(k_stem_pool(S.raw0, B, bnstat(S, d.stem_bn.idx, BS_SCALE), bnstat(S, d.stem_bn.idx, BS_SHIFT), S.a0, s));
     // residual stages                                            (resnet.py:31-47, 99-102)
@@ -432,28 +510,28 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
             // conv1 -> BN -> ReLU -> split activation in one kernel; conv2 -> BN -> (+identity) -> ReLU likewise
             ConvEpilogue e1 = conv_ep(1);
             e1.scale = bnstat(S, P.b1.idx, BS_SCALE); e1.shift = bnstat(S, P.b1.idx, BS_SHIFT); e1.relu = 1; e1.out_split = A.b1;
-            TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[s1], P.planes, 9, nullptr, e1, s));
+            TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[s1], P.planes, 9, nullptr, e1, L));
             ConvEpilogue e2 = conv_ep(1);
             e2.scale = bnstat(S, P.b2.idx, BS_SCALE); e2.shift = bnstat(S, P.b2.idx, BS_SHIFT); e2.relu = 1; e2.out_split = A.out;
             if (P.has_ds) {
                 ConvEpilogue ed = conv_ep(1);
                 ed.scale = bnstat(S, P.bds.idx, BS_SCALE); ed.shift = bnstat(S, P.bds.idx, BS_SHIFT);
-                TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[conv_slot(d, P.ds.w)], P.planes, 1, A.rawd, ed, s));
+                TRY(conv_any(c, be, in, R25, P.cin, pw->fwd[conv_slot(d, P.ds.w)], P.planes, 1, A.rawd, ed, L));
                 e2.add_prev = A.rawd;
             } else {
                 e2.res = in;
             }
-            TRY(conv_any(c, be, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, nullptr, e2, s));
+            TRY(conv_any(c, be, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, nullptr, e2, L));
             in = A.out;
             continue;
         }
-        TRY(conv_bn(c, S, in, R25, P.cin, pw->fwd[s1], P.planes, 9, A.raw1, 1, P.b1, cnt24, params, bn, nbt, -1, training, s));
+        TRY(conv_bn(c, S, in, R25, P.cin, pw->fwd[s1], P.planes, 9, A.raw1, 1, P.b1, cnt24, params, bn, nbt, -1, training, L));
         TRY(k_bn_apply(A.raw1, R25, P.planes, bnstat(S, P.b1.idx, BS_SCALE), bnstat(S, P.b1.idx, BS_SHIFT), 0, none, nullptr,
                        nullptr, nullptr, 1, A.b1, s));
-        TRY(conv_bn(c, S, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, A.raw2, 1, P.b2, cnt24, params, bn, nbt, -1, training, s));
+        TRY(conv_bn(c, S, A.b1, R25, P.planes, pw->fwd[s2], P.planes, 9, A.raw2, 1, P.b2, cnt24, params, bn, nbt, -1, training, L));
         if (P.has_ds) {
             TRY(conv_bn(c, S, in, R25, P.cin, pw->fwd[conv_slot(d, P.ds.w)], P.planes, 1, A.rawd, 1, P.bds, cnt24, params, bn, nbt, -1,
-                        training, s));
+                        training, L));
             TRY(k_bn_apply(A.raw2, R25, P.planes, bnstat(S, P.b2.idx, BS_SCALE), bnstat(S, P.b2.idx, BS_SHIFT), 2, none, A.rawd,
                            bnstat(S, P.bds.idx, BS_SCALE), bnstat(S, P.bds.idx, BS_SHIFT), 1, A.out, s));
         } else {
@@ -464,10 +542,10 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     }
     // head                                                       (networks.py:18-26)
     TRY(conv_bn(c, S, in, R25, 512, pw->fwd[conv_slot(d, d.h1.w)], 128, 1, S.raw_h1, 1, d.hbn1, cnt24, params, bn, nbt, d.h1_bias,
-                training, s));
+                training, L));
     TRY(k_head_up1(S.raw_h1, B, bnstat(S, d.hbn1.idx, BS_SCALE), bnstat(S, d.hbn1.idx, BS_SHIFT), S.u1, s));
     TRY(conv_bn(c, S, S.u1, R48, 128, pw->fwd[conv_slot(d, d.h2.w)], 32, 1, S.raw_h2, 0, d.hbn2, cnt48, params, bn, nbt, d.h2_bias,
-                training, s));
+                training, L));
     TRY(k_head_t(S.raw_h2, R48, bnstat(S, d.hbn2.idx, BS_SCALE), bnstat(S, d.hbn2.idx, BS_SHIFT), params + d.poff[d.h3.w], d.A,
                  S.t, s));
     if (q) TRY(k_head_up2(S.t, B, d.A, params + d.poff[d.h3_bias], q, s));
@@ -490,24 +568,25 @@ extern "C" int simq_fcn_forward(simq_ctx* c, const float* params, float* bn, int
     int err;
     PackedSet* pw = get_packed(c, params, params_version, s, &err);
     if (err) return 1;
-    return run_forward(c, pw, params, bn, nbt, x, B, x_layout, training, c->set[save_for_backward ? 0 : 1], q, s);
+    return run_forward(c, pw, params, bn, nbt, x, B, x_layout, training, c->set[save_for_backward ? 0 : 1], q, main_lane(c, s));
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// nparts > 0: the dgrad epilogue that produced G already left `nparts` rows of (sum dz, sum dz*xhat) in c->partials
+// nparts > 0: the dgrad epilogue that produced G already left `nparts` rows of (sum dz, sum dz*xhat) in L.partials
 static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, long long rows, double count, int mask_mode,
                        const bf16* mask_hi, const float* raw, const float* params, float* grads, int pitch25, Split dy,
-                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, cudaStream_t s) {
+                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, const Lane& L) {
     const NetDesc& d = c->d;
+    cudaStream_t s = L.s;
     if (nparts > 0) {
-        TRY(k_reduce_partials(c->partials, nparts, 2 * b.ch, c->sums, 1.0f, s));
+        TRY(k_reduce_partials(L.partials, nparts, 2 * b.ch, c->sums, 1.0f, s));
     } else {
         TRY(k_bn_bwd_reduce(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
                             bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr,
-                            bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr, c->partials, s));
-        TRY(k_reduce_partials(c->partials, STAT_BLOCKS, 3 * b.ch, c->sums, 1.0f, s));
+                            bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr, L.partials, s));
+        TRY(k_reduce_partials(L.partials, STAT_BLOCKS, 3 * b.ch, c->sums, 1.0f, s));
     }
     TRY(k_bn_bwd_apply(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
                        bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), params + d.poff[b.gamma], c->sums, count, pitch25, dy,
@@ -517,12 +596,17 @@ static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, lon
     return 0;
 }
 
-static int bias_grad(simq_ctx* c, Split dy, long long rows, int ch, float* out, cudaStream_t s) {
-    TRY(k_colsum_split(dy, rows, ch, c->partials, s));
-    TRY(k_reduce_partials(c->partials, STAT_BLOCKS, ch, out, 1.0f, s));
+static int bias_grad(simq_ctx* c, Split dy, long long rows, int ch, float* out, const Lane& L) {
+    TRY(k_colsum_split(dy, rows, ch, L.partials, L.s));
+    TRY(k_reduce_partials(L.partials, STAT_BLOCKS, ch, out, 1.0f, L.s));
     return 0;
 }
 
+// The backward pass.  Lane M (the caller's stream) runs the chain that carries the gradient from layer to layer --
+// BatchNorm backward (-> dy of the conv below it) and the dgrad GEMMs; every weight-gradient GEMM only needs that dy and a
+// saved activation, so it is handed to lane W.  The dy operand buffers are the hand-over points: dyA ping-pongs with dyA2
+// (lane M may fill the next dy while lane W still reads the previous one), and before any dy buffer is rewritten lane M
+// waits for the weight gradient that last read it (ev_done).  Lane W is joined before returning.
 static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const float* x, int x_layout, const float* dq, int B,
                         float* grads, cudaStream_t s) {
     const NetDesc& d = c->d;
@@ -532,6 +616,26 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
     const int be = c->backend, A = d.A;
     Split none{nullptr, nullptr};
+    cudaStream_t ws;
+    TRY(side_stream_for(c, s, &ws));
+    const Lane M = main_lane(c, s), W = side_lane(c, ws);
+    const bool two = ws != s;
+    enum { BUF_A0 = 0, BUF_A1 = 1, BUF_B = 2, BUF_MISC = 3 };
+    bool pending[4] = {false, false, false, false};
+    Split dyA[2] = {c->dyA, two ? c->dyA2 : c->dyA};
+    int cur = 1;                                         // index of the dyA buffer written last
+    // lane M is about to overwrite dy buffer `buf`: wait for the weight gradient that read it
+    auto acquire = [&](int buf) -> int {
+        if (two && pending[buf]) { SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_done[buf], 0)); pending[buf] = false; }
+        return 0;
+    };
+    // weight gradient of one conv on lane W, ordered after everything lane M has enqueued so far (dy is complete)
+    auto wgrad_on_w = [&](int buf, Split dY, Split X, long long rows, int Cout, int Cin, int ntaps, float* dW) -> int {
+        TRY(lane_order(c, s, ws));
+        TRY(wgrad_any(c, be, dY, X, rows, Cout, Cin, ntaps, dW, W));
+        if (two) { SIMQ_CUDA(cudaEventRecord(c->ev_done[buf], ws)); pending[buf] = true; }
+        return 0;
+    };
     // ---- head: upsample adjoint, conv3 + BN2 + conv2 ----
     TRY(k_up2_adj(dq, B, A, c->dt, s));
     const int hb2 = d.hbn2.idx;
@@ -543,17 +647,18 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                         grads + d.poff[d.h3_bias], s));
     TRY(k_head2_apply(c->dt, S.raw_h2, R48, A, bnstat(S, hb2, BS_SCALE), bnstat(S, hb2, BS_SHIFT), bnstat(S, hb2, BS_MEAN),
                       bnstat(S, hb2, BS_INVSTD), params + d.poff[d.h3.w], c->sums, cnt48, c->dy2h, s));
-    TRY(bias_grad(c, c->dy2h, R48, 32, grads + d.poff[d.h2_bias], s));
-    TRY(wgrad_any(c, be, c->dy2h, S.u1, R48, 32, 128, 1, grads + d.poff[d.h2.w], s));
+    TRY(wgrad_on_w(BUF_MISC, c->dy2h, S.u1, R48, 32, 128, 1, grads + d.poff[d.h2.w]));
+    TRY(bias_grad(c, c->dy2h, R48, 32, grads + d.poff[d.h2_bias], M));
     ConvEpilogue ep0 = conv_ep(0);
-    TRY(conv_any(c, be, c->dy2h, R48, 32, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, s));
+    TRY(conv_any(c, be, c->dy2h, R48, 32, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     float* G = c->G[0];
     float* Gn = c->G[1];
     TRY(k_up1_adj(c->du1, B, G, s));
-    TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr, none, 0, s));
-    TRY(bias_grad(c, c->dyA, R25, 128, grads + d.poff[d.h1_bias], s));
-    TRY(wgrad_any(c, be, c->dyA, S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w], s));
+    cur ^= 1; TRY(acquire(cur));
+    TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr, none, 0, M));
+    TRY(wgrad_on_w(cur, dyA[cur], S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w]));
+    TRY(bias_grad(c, dyA[cur], R25, 128, grads + d.poff[d.h1_bias], M));
     ConvEpilogue ep25 = conv_ep(1);
     // With the tcgen05 back-end the dgrad launch that PRODUCES a gradient also reduces the BatchNorm-backward sums of
     // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
@@ -563,7 +668,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
     auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
         if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
-            e.stats = c->partials; e.bn_raw = raw; e.bn_mask = mask;
+            e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask;
             e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
         }
         return e;
@@ -571,7 +676,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     int g_parts = 0;                 // partial rows already available for the BN consuming G
     {
         ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
-        TRY(conv_any(c, be, c->dyA, R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, s));
+        TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M));
         g_parts = e.bn_raw ? nparts_fused : 0;
     }
     { float* t = G; G = Gn; Gn = t; }
@@ -582,16 +687,19 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         Split in = b == 0 ? S.a0 : S.blk[b - 1].out;
         const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
         // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
-        TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, c->dyA, nullptr, P.has_ds ? &P.bds : nullptr,
-                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, s));
-        TRY(wgrad_any(c, be, c->dyA, Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w], s));
+        cur ^= 1; TRY(acquire(cur));
+        if (P.has_ds) TRY(acquire(BUF_B));
+        TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, dyA[cur], nullptr, P.has_ds ? &P.bds : nullptr,
+                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, M));
+        TRY(wgrad_on_w(cur, dyA[cur], Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w]));
+        if (P.has_ds) TRY(wgrad_on_w(BUF_B, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w]));
         ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
-        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, s));
-        if (P.has_ds) TRY(wgrad_any(c, be, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w], s));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M));
         // b1 = relu(bn1(raw1))
-        TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, c->dyA, nullptr, nullptr, nullptr,
-                        none, em.bn_raw ? nparts_fused : 0, s));
-        TRY(wgrad_any(c, be, c->dyA, in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w], s));
+        cur ^= 1; TRY(acquire(cur));
+        TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
+                        none, em.bn_raw ? nparts_fused : 0, M));
+        TRY(wgrad_on_w(cur, dyA[cur], in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w]));
         // gradient w.r.t. the block input = the previous block's output (or the stem's pooled output for b == 0)
         const bool consumer_fusable = b > 0 && !d.blk[b - 1].has_ds;
         ConvEpilogue ep = ep25;
@@ -601,7 +709,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
             ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
             g_parts = ep.bn_raw ? nparts_fused : 0;
         }
-        TRY(conv_any(c, be, c->dyA, R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, s));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M));
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
@@ -609,7 +717,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                 epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
                 g_parts = epd.bn_raw ? nparts_fused : 0;
             }
-            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, s));
+            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M));
         }
         { float* t = G; G = Gn; Gn = t; }
     }
@@ -617,13 +725,14 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     const int sb = d.stem_bn.idx;
     TRY(k_pool_bwd(G, S.raw0, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
     if (be == SIMQ_BACKEND_UMMA) {
-        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, 0, s));
-        TRY(wgrad_any(c, be, c->dy0s, S.acol, R48, 64, stem_kp(d.C), 1, c->stem_tmp, s));
-        TRY(k_strip_stem(c->stem_tmp, d.C, stem_kp(d.C), grads + d.poff[d.stem.w], s));
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, 0, M));
+        TRY(wgrad_on_w(BUF_MISC, c->dy0s, S.acol, R48, 64, stem_kp(d.C), 1, c->stem_tmp));
+        TRY(k_strip_stem(c->stem_tmp, d.C, stem_kp(d.C), grads + d.poff[d.stem.w], ws));
     } else {
-        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, 0, s));
+        TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, none, c->dy0, nullptr, nullptr, none, 0, M));
         TRY(k_stem_wgrad(x, x_layout, B, d.C, c->dy0, c->stem_partials, grads + d.poff[d.stem.w], s));
     }
+    TRY(lane_order(c, ws, s));                            // join: every weight gradient is in `grads` for what follows on s
     return 0;
 }
 
@@ -666,20 +775,37 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
     int err;
     PackedSet* pw = get_packed(c, params, 0, s, &err);                                     // SGD changed them last step
     if (err) return 1;
-    // train.py:114  online forward on s (train-mode BN, activations kept)
-    TRY(run_forward(c, pw, params, bn, nbt, s_, B, x_layout, 1, c->set[0], c->q_s, s));
+    PackedSet* pt = nullptr;
     if (Bn > 0) {
-        // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again)
-        if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, s));
-        // train.py:122/124  target forward, eval-mode BN
-        PackedSet* pt = get_packed(c, target_params, target_version, s, &err);
+        pt = get_packed(c, target_params, target_version, s, &err);
         if (err) return 1;
-        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, s,
-                        /*reuse_acol=*/double_dqn != 0));     // the online pass just expanded the same s' into set[1]
         pw = nullptr;
         for (int i = 0; i < 2; ++i)
             if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];
         if (!pw) { simq_set_error("simq_train_step: packed policy weights evicted"); return 1; }
+    }
+    // The three forwards are independent: lane A (this stream) runs the s pass, lane B the two s' passes.
+    cudaStream_t bs;
+    TRY(side_stream_for(c, s, &bs));
+    const Lane LA = main_lane(c, s);
+    Lane LB = side_lane(c, bs);
+    const bool two = bs != s && Bn > 0;
+    if (two) TRY(lane_order(c, s, bs));                                                    // fork (after the weight packing)
+    // train.py:114  online forward on s (train-mode BN, activations kept)
+    TRY(run_forward(c, pw, params, bn, nbt, s_, B, x_layout, 1, c->set[0], c->q_s, LA));
+    if (Bn > 0) {
+        // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again: after the
+        // s pass's update, so a concurrent s' pass stashes its batch statistics and they are applied after the join)
+        if (two) LB.defer = c->bn_defer;
+        if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, LB));
+        LB.defer = nullptr;
+        // train.py:122/124  target forward, eval-mode BN
+        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, LB,
+                        /*reuse_acol=*/double_dqn != 0));     // the online pass just expanded the same s' into set[1]
+        if (two) {
+            TRY(lane_order(c, bs, s));                                                     // join
+            if (double_dqn) TRY(k_bn_running_update_all(c->bn_table, SIMQ_N_BN, c->bn_defer, bn, (long long*)nbt, s));
+        }
     }
     // train.py:115-129; dL/dQ is one-hot per sample
     float* dq = c->dq;
@@ -836,7 +962,7 @@ extern "C" int simq_intention_step(simq_ctx* c, float* params, float* bn, int64_
             PackedSet* pw = get_packed(c, params, 0, s, &err);
             if (err) return 1;
             // train.py:145-148: inputs = all channels but the last, target = the last channel of the same state
-            TRY(run_forward(c, pw, params, bn, nbt, state, B, SIMQ_X_NHWC_PLUS1, 1, c->set[0], c->q_s, s));
+            TRY(run_forward(c, pw, params, bn, nbt, state, B, SIMQ_X_NHWC_PLUS1, 1, c->set[0], c->q_s, main_lane(c, s)));
             TRY(k_bce_tail(c->q_s, state + c->d.C, c->d.C + 1, (long long)B * 9216, out1, c->dq, c->dpartials, s));     // :149-150
             TRY(run_backward(c, pw, params, state, SIMQ_X_NHWC_PLUS1, c->dq, B, grads, s));                              // :151-152
             if (apply_update)                                                                                           // :153
@@ -860,7 +986,7 @@ extern "C" int simq_greedy_action(simq_ctx* c, const float* params, const float*
             PackedSet* pw = get_packed(c, params, params_version, s, &err);
             if (err) return 1;
             float* qq = q ? q : c->q_nt;
-            TRY(run_forward(c, pw, params, (float*)bn, nullptr, x, B, x_layout, 0, c->set[1], qq, s));
+            TRY(run_forward(c, pw, params, (float*)bn, nullptr, x, B, x_layout, 0, c->set[1], qq, main_lane(c, s)));
             return k_argmax_rows(qq, B, (long long)c->d.A * 9216, (long long*)action_out, s);
         },
         [&]() { packed_set_version(c, params, params_version); });
@@ -923,16 +1049,16 @@ extern "C" int simq_test_conv(simq_ctx* c, int backend, int mode, int B, int Cin
     if (mode == 0) {
         TRY(k_import_p25(a, B, Cin, X, nullptr, s));
         TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));
-        TRY(conv_any(c, backend, X, R25, Cin, wf, Cout, taps, c->G[0], ep25, s));
+        TRY(conv_any(c, backend, X, R25, Cin, wf, Cout, taps, c->G[0], ep25, main_lane(c, s)));
         return k_export_p25(c->G[0], none, B, Cout, out, s);
     } else if (mode == 1) {
         TRY(k_import_p25(a, B, Cout, Y, nullptr, s));
         TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));
-        TRY(conv_any(c, backend, Y, R25, Cout, wb, Cin, taps, c->G[0], ep25, s));
+        TRY(conv_any(c, backend, Y, R25, Cout, wb, Cin, taps, c->G[0], ep25, main_lane(c, s)));
         return k_export_p25(c->G[0], none, B, Cin, out, s);
     } else {
         TRY(k_import_p25(a, B, Cin, X, nullptr, s));
         TRY(k_import_p25(a2, B, Cout, Y, nullptr, s));
-        return wgrad_any(c, backend, Y, X, R25, Cout, Cin, taps, out, s);
+        return wgrad_any(c, backend, Y, X, R25, Cout, Cin, taps, out, side_lane(c, s));
     }
 }

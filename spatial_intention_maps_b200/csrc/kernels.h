@@ -8,10 +8,12 @@
 // ---- forward elementwise (kernels_elem.cu) ----
 int k_colstats(const float* x, long long rows, int C, float* partials, cudaStream_t s);
 int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
-                        const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
+                        const float* conv_bias, float* rmean, float* rvar, long long* nbt, double* defer, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s);
 // every BatchNorm of the network in one launch (block = one BN): scale/shift into bnstat[(idx*4 + 2|3) * MAX_CH]
 struct BnEntry { long long gamma_off, bias_off /* -1: none */, bn_off; int ch, idx; };
+// applies the running-statistics updates a pass stashed in `defer` (k_bn_finalize_train with defer != NULL)
+int k_bn_running_update_all(const BnEntry* table_dev, int n, const double* defer, float* bn, long long* nbt, cudaStream_t s);
 int k_bn_eval_affine_all(const float* params, const float* bn, const BnEntry* table_dev, int n, float* bnstat, cudaStream_t s);
 int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* conv_bias, const float* rmean,
                      const float* rvar, float* scale, float* shift, cudaStream_t s);

@@ -47,6 +47,12 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
     return 0;
 }
 
+// running = (1 - momentum) * running + momentum * batch_value, with the rounding of every operation pinned (no
+// compiler-chosen FMA contraction): the immediate and the deferred update must agree bit for bit.
+__device__ __forceinline__ float bn_running_mix(float running, double batch_value) {
+    return (float)__dadd_rn(__dmul_rn(1.0 - BN_MOM, (double)running), __dmul_rn(BN_MOM, batch_value));
+}
+
 // nn.BatchNorm2d train-mode bookkeeping (eps 1e-5, momentum 0.1, unbiased var into running_var,
 // num_batches_tracked += 1).  `raw` excludes the conv bias: the batch mean of the true conv output is
 // mean_raw + bias, and the bias cancels in the normalised value.
@@ -56,7 +62,7 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
 __global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          const float* __restrict__ conv_bias, float* rmean, float* rvar,
-                                         long long* nbt, float* mean, float* invstd, float* scale, float* shift) {
+                                         long long* nbt, double* defer, float* mean, float* invstd, float* scale, float* shift) {
     __shared__ double sS[32][33], sSS[32][33];
     const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -93,17 +99,44 @@ __global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __
     float sc = g * is;
     scale[c] = sc;
     shift[c] = b - (float)m * sc;
-    rmean[c] = (float)((1.0 - BN_MOM) * (double)rmean[c] + BN_MOM * (m + (double)bias));
     double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    rvar[c] = (float)((1.0 - BN_MOM) * (double)rvar[c] + BN_MOM * unbiased);
+    if (defer) {            // a concurrent pass owns the running statistics right now: bn_running_update_all applies these later
+        defer[c] = m + (double)bias;
+        defer[MAX_CH + c] = unbiased;
+        return;
+    }
+    rmean[c] = bn_running_mix(rmean[c], m + (double)bias);
+    rvar[c] = bn_running_mix(rvar[c], unbiased);
     if (c == 0 && nbt) nbt[0] += 1;
 }
 
 int k_bn_finalize_train(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
-                        const float* conv_bias, float* rmean, float* rvar, long long* nbt, float* mean,
+                        const float* conv_bias, float* rmean, float* rvar, long long* nbt, double* defer, float* mean,
                         float* invstd, float* scale, float* shift, cudaStream_t s) {
     bn_finalize_train_kernel<<<ceil_div(C, 32), 1024, 0, s>>>(partials, nparts, C, count, gamma, beta, conv_bias, rmean, rvar,
-                                                              nbt, mean, invstd, scale, shift);
+                                                              nbt, defer, mean, invstd, scale, shift);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
+// The running-statistics update of every BatchNorm of one train-mode pass from the stash bn_finalize_train_kernel left
+// in `defer` ([n][2][MAX_CH] doubles: batch mean incl. conv bias, unbiased batch variance): the same arithmetic, applied
+// after the pass that ran concurrently (one block per BN).
+__global__ void __launch_bounds__(MAX_CH) bn_running_update_all_kernel(const BnEntry* __restrict__ table, const double* __restrict__ defer,
+                                                                       float* __restrict__ bn, long long* __restrict__ nbt) {
+    const BnEntry E = table[blockIdx.x];
+    const int c = threadIdx.x;
+    if (c >= E.ch) return;
+    const double* d = defer + (size_t)E.idx * 2 * MAX_CH;
+    float* rmean = bn + E.bn_off;
+    float* rvar = rmean + E.ch;
+    rmean[c] = bn_running_mix(rmean[c], d[c]);
+    rvar[c] = bn_running_mix(rvar[c], d[MAX_CH + c]);
+    if (c == 0 && nbt) nbt[E.idx] += 1;
+}
+
+int k_bn_running_update_all(const BnEntry* table_dev, int n, const double* defer, float* bn, long long* nbt, cudaStream_t s) {
+    bn_running_update_all_kernel<<<n, MAX_CH, 0, s>>>(table_dev, defer, bn, nbt);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }

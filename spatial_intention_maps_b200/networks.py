@@ -194,6 +194,8 @@ class FCN(nn.Module):
                 _lib.check(_lib.lib().simq_set_backend(self._ctx.handle, self._backend), 'simq_set_backend')
             if getattr(self, '_precision', None) is not None:
                 _lib.check(_lib.lib().simq_set_precision(self._ctx.handle, self._precision), 'simq_set_precision')
+            if getattr(self, '_schedule', None) is not None:
+                _lib.check(_lib.lib().simq_set_schedule(self._ctx.handle, self._schedule), 'simq_set_schedule')
         return self._ctx
 
     def set_backend(self, backend: int):
@@ -206,6 +208,13 @@ class FCN(nn.Module):
         m = {'parity': _lib.PRECISION_PARITY, 'bf16': _lib.PRECISION_BF16}[mode]
         self._precision = m
         _lib.check(_lib.lib().simq_set_precision(self.ctx().handle, m), 'simq_set_precision')
+
+    def set_schedule(self, mode: str):
+        """'lanes' (default: independent pieces of a step on two streams / graph branches) or 'serial' (one stream, the
+        reference's order).  Bit-identical results; 'serial' exists for A/B timing and debugging."""
+        m = {'serial': _lib.SCHEDULE_SERIAL, 'lanes': _lib.SCHEDULE_LANES}[mode]
+        self._schedule = m
+        _lib.check(_lib.lib().simq_set_schedule(self.ctx().handle, m), 'simq_set_schedule')
 
     @staticmethod
     def _x_layout(x):

@@ -228,6 +228,70 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     assert torch.equal(results[0][3], results[1][3])
 
 
+@pytest.mark.parametrize('graph', ['1', '0'], ids=['graph', 'eager'])
+@pytest.mark.parametrize('B,C,A,double_dqn', [(8, 4, 2, True), (37, 10, 1, True), (8, 5, 2, False)])
+def test_lane_schedule_is_bit_identical_to_serial(monkeypatch, graph, B, C, A, double_dqn):
+    """The two-lane schedule (forward on s beside the forwards on s', weight gradients beside the dgrad chain;
+    two branches of the CUDA graph) must leave exactly the losses, parameters, momentum, BN running statistics and
+    counters of the serial schedule over six updates -- incl. an all-terminal batch (no s' lane), two non-terminal
+    counts, a target sync, the plain-DQN branch (only the target pass on the s' lane), and the deferred
+    running-statistics update of the concurrent s' pass."""
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    monkeypatch.setenv('SIMQ_GRAPH', graph)
+    results = []
+    for sched in ('lanes', 'serial'):
+        net, st = G.make_net(C, A, 29, max_batch=B)
+        net.set_schedule(sched)
+        tgt = networks.FCN(C, A, max_batch=B)
+        tgt.load_state_dict(st)
+        tgt = tgt.to(G.DEV).eval()
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        cfg = G.Cfg(B, C)
+        cfg.use_double_dqn = double_dqn
+        nbt0 = int(net.flat_nbt[0])
+        out = []
+        for step in range(6):
+            te = 1 if step == 3 else (4 if step % 2 else 8)       # step 3: every transition terminal
+            batch = synth.synth_batch(B, C, A, 300 + step, terminal_every=te)
+            if step == 4:
+                tgt.load_state_dict(net.state_dict())
+            r = T.train(cfg, net, tgt, opt, batch, None, 0.85)
+            out.append((r['loss'], r['td_error']))
+        results.append((out, net.flat_params.clone(), net.flat_bn.clone(), net.flat_nbt.clone(), net.flat_momentum.clone()))
+    assert results[0][0] == results[1][0]
+    for i, name in ((1, 'params'), (2, 'bn'), (3, 'nbt'), (4, 'momentum')):
+        a, b = results[0][i], results[1][i]
+        assert torch.equal(a, b), (name, int((a != b).sum()), float((a.double() - b.double()).abs().max()),
+                                   (a != b).nonzero().flatten()[:8].tolist())
+    assert int(results[0][3][0]) == nbt0 + 6 + (5 if double_dqn else 0)      # +1 per s pass, +1 per s' online pass
+
+
+def test_lane_schedule_autograd_and_intention_paths():
+    """The weight-gradient lane also serves simq_fcn_backward (stock autograd route) and simq_intention_step:
+    gradients / updated parameters equal the serial schedule bit for bit."""
+    from spatial_intention_maps_b200 import synth, train as T
+    grads, params = [], []
+    for sched in ('lanes', 'serial'):
+        net, _ = G.make_net(5, 2, 31, max_batch=6)
+        net.set_schedule(sched)
+        net.train()
+        x = torch.from_numpy(np.stack(synth.synth_states(6, 5, 77))).to(G.DEV).permute(0, 3, 1, 2)
+        q = net(x)
+        q.square().mean().backward()
+        grads.append(net.flat_grad().clone())
+        inet, _ = G.make_net(4, 1, 33, max_batch=6)
+        inet.set_schedule(sched)
+        inet.train()
+        opt = torch.optim.SGD(inet.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        batch = synth.synth_batch(6, 5, 1, 55, terminal_every=8)
+        for _ in range(3):
+            T.train_intention(inet, opt, batch, None)
+        params.append(inet.flat_params.clone())
+    assert torch.equal(grads[0], grads[1])
+    assert torch.equal(params[0], params[1])
+
+
 def test_bf16_mode_is_characterised_and_not_default():
     """simq_set_precision(BF16) -- one MMA per product -- is opt-in: its Q-map error is of the order SURVEY.md
     §7.2-1 predicts for bf16 operands (1e-2: outside the 1e-3 parity bar), the default mode is untouched by it."""
