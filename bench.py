@@ -180,13 +180,15 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    v, per_step, cores = cpu_steps(steps, warmup)
-    sample = (f'{steps} timed + {warmup} warm-up steps of batch {CPU_SAMPLE_B} (same network C={C_IN} A={A_OUT}, double-DQN; '
-              f'CPU samples/s is flat in batch size, BASELINE.md §2), torch CPU fp32, {cores} threads')
+    # bounded sample: batches of 16 -- the size at which the CPU path is FASTEST per sample (measured on the 16-core box:
+    # 38.5 samples/s at batch 16, 29.2 at the config's batch 128, which no longer fits the caches) -- at most 40 timed steps
+    steps, warmup, Bc = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3)), CPU_SAMPLE_B
+    v, per_step, cores = cpu_steps(steps, warmup, Bc)
+    sample = (f'{steps} timed + {warmup} warm-up steps of batch {Bc} (same network C={C_IN} A={A_OUT}, double-DQN, every 8th transition '
+              f'terminal), oracle port of train.train, torch CPU fp32, {cores} threads')
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
             'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic', 'config': {'workload': workload_name(args.batch), 'cpu_sample_batch': CPU_SAMPLE_B},
+            'data': 'synthetic', 'config': {'workload': workload_name(args.batch), 'cpu_sample_batch': Bc},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -405,9 +407,9 @@ def run_simq(args):
         }
         if world == 1 and not args.no_cpu:
             try:
-                v, per, cores = cpu_steps(3, 1)
+                v, per, cores = cpu_steps(24, 2)             # ~10 s of CPU work
                 line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                        'sample': f'3 timed + 1 warm-up steps of batch {CPU_SAMPLE_B} of the same step (oracle port of train.train, torch CPU fp32)'}
+                                        'sample': f'24 timed + 2 warm-up steps of batch {CPU_SAMPLE_B} of the same step (oracle port of train.train, torch CPU fp32)'}
             except Exception as e:  # noqa: BLE001
                 line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {type(e).__name__}: {e}'}
         print(json.dumps(line), flush=True)

@@ -181,10 +181,9 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
     policy._manual_version += 1
 
 
-def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_factor):
-    """train.py:108-141 with the same arguments.  ``transform_fn`` is accepted for signature
-    compatibility; states are staged NHWC (``ToTensor`` on float32 input is only a transpose,
-    policies.py:44-45, which the stem kernel absorbs)."""
+def _enqueue_train(cfg, policy_net, target_net, optimizer, batch, discount_factor) -> DeviceBatch:
+    """Stage ``batch`` and enqueue one update on the current stream; (loss, td_error) land in the returned
+    DeviceBatch's pinned ``out2_host`` once the stream has run (no synchronisation here)."""
     policy, target = _unwrap(policy_net), _unwrap(target_net)
     B = int(cfg.batch_size)
     C = policy.num_input_channels
@@ -210,15 +209,53 @@ def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_
     train_step_device(policy, target, optimizer, db, B, discount_factor, getattr(cfg, 'grad_norm_clipping', None),
                       bool(getattr(cfg, 'use_double_dqn', True)))
     db.out2_host.copy_(db.out2, non_blocking=True)
+    return db
+
+
+def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_factor):
+    """train.py:108-141 with the same arguments.  ``transform_fn`` is accepted for signature
+    compatibility; states are staged NHWC (``ToTensor`` on float32 input is only a transpose,
+    policies.py:44-45, which the stem kernel absorbs)."""
+    db = _enqueue_train(cfg, policy_net, target_net, optimizer, batch, discount_factor)
     torch.cuda.current_stream().synchronize()       # the reference syncs here too: two .item() calls (train.py:138-139)
     return {'td_error': float(db.out2_host[1]), 'loss': float(db.out2_host[0])}
 
 
-def train_intention(intention_net, optimizer, batch, transform_fn):
-    """train.py:143-158 with the same arguments: one supervised update of the intention-prediction net
-    ``FCN(C-1, 1)`` -- input = all channels of ``batch.state`` but the last, target = the last channel,
-    ``BCEWithLogitsLoss`` (mean), backward, plain momentum-SGD (no clipping) -- as ONE call into the library
-    (``simq_intention_step``).  Returns ``{'loss_intention': float}``."""
+def train_groups(cfg, policy, target_nets, optimizers, batches, optimizers_intention=None):
+    """The per-timestep training block of the reference's main loop (train.py:253-263; the same loop is
+    ``Trainer.step``, train_multiprocess.py:366-377): one update per robot group -- ``policy.policy_nets[i]`` against
+    ``target_nets[i]`` on ``batches[i]`` with ``cfg.discount_factors[i]``, plus the group's intention net when
+    ``cfg.use_predicted_intention`` -- returning the reference's ``all_train_info`` dict
+    (``'{name}/robot_group_{i+1:02}'`` -> float).  The updates of all groups are enqueued back to back (each network has
+    its own context and workspace) and the host waits ONCE, instead of two ``.item()`` round trips per group."""
+    n = policy.num_robot_groups
+    if not (len(target_nets) == len(optimizers) == len(batches) == n):
+        raise ValueError(f'expected {n} target nets / optimizers / batches')
+    use_int = bool(getattr(cfg, 'use_predicted_intention', False))
+    if use_int and (optimizers_intention is None or len(optimizers_intention) != n):
+        raise ValueError('cfg.use_predicted_intention needs one intention optimizer per robot group')
+    pending = []
+    for i in range(n):
+        db = _enqueue_train(cfg, policy.policy_nets[i], target_nets[i], optimizers[i], batches[i], cfg.discount_factors[i])
+        ic = _enqueue_intention(policy.intention_nets[i], optimizers_intention[i], _as_transition(batches[i])) if use_int else None
+        pending.append((db, ic))
+    torch.cuda.current_stream().synchronize()
+    info = {}
+    for i, (db, ic) in enumerate(pending):
+        tag = 'robot_group_{:02}'.format(i + 1)
+        info[f'td_error/{tag}'] = float(db.out2_host[1])
+        info[f'loss/{tag}'] = float(db.out2_host[0])
+        if ic is not None:
+            info[f'loss_intention/{tag}'] = float(ic['out_host'][0])
+    return info
+
+
+def _as_transition(batch):
+    from .replay import DeviceSample
+    return batch.to_transition() if isinstance(batch, DeviceSample) else batch
+
+
+def _enqueue_intention(intention_net, optimizer, batch):
     net = _unwrap(intention_net)
     B = len(batch.state)
     Ct = net.num_input_channels + 1
@@ -239,6 +276,15 @@ def train_intention(intention_net, optimizer, batch, transform_fn):
     cache['dev'].copy_(cache['host'], non_blocking=True)
     intention_step_device(net, optimizer, cache['dev'], B, cache['out'])
     cache['out_host'].copy_(cache['out'], non_blocking=True)
+    return cache
+
+
+def train_intention(intention_net, optimizer, batch, transform_fn):
+    """train.py:143-158 with the same arguments: one supervised update of the intention-prediction net
+    ``FCN(C-1, 1)`` -- input = all channels of ``batch.state`` but the last, target = the last channel,
+    ``BCEWithLogitsLoss`` (mean), backward, plain momentum-SGD (no clipping) -- as ONE call into the library
+    (``simq_intention_step``).  Returns ``{'loss_intention': float}``."""
+    cache = _enqueue_intention(intention_net, optimizer, batch)
     torch.cuda.current_stream().synchronize()
     return {'loss_intention': float(cache['out_host'][0])}
 

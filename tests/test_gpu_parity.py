@@ -292,6 +292,58 @@ def test_lane_schedule_autograd_and_intention_paths():
     assert torch.equal(params[0], params[1])
 
 
+def test_c4_two_robot_groups_training_block_matches_oracle():
+    """Config c4 (lifting_2_pushing_2: two robot groups -> an A=2 and an A=1 Q-network, gamma 0.85 each, predicted
+    intention on -> two intention nets): ``train.train_groups`` -- the training block of the reference's main loop
+    (train.py:253-263), all four updates enqueued back to back, one host sync -- returns the reference's
+    ``all_train_info`` keys with losses within 1e-3 of the oracle's and leaves the networks bit-identical to four
+    separate ``train`` / ``train_intention`` calls."""
+    from oracle import fcn_oracle as O
+    from spatial_intention_maps_b200 import policies, synth, train as T
+    B, C = 8, 5
+    cfg = G.Cfg(B, C)
+    cfg.robot_config = [{'lifting_robot': 2}, {'pushing_robot': 2}]
+    cfg.discount_factors = [0.85, 0.85]
+    cfg.use_predicted_intention = True
+    outs = []
+    for grouped in (True, False):
+        pol = policies.DQNIntentionPolicy(cfg, train=True, device=G.DEV)
+        assert [n.module.num_output_channels for n in pol.policy_nets] == [2, 1]
+        states = []
+        for i, net in enumerate(pol.policy_nets + pol.intention_nets):
+            st = O.make_state(net.module.num_input_channels, net.module.num_output_channels, 40 + i)
+            net.module.load_state_dict(st)
+            net.train()
+            states.append(st)
+        tgts = pol.build_policy_nets()
+        for t, n in zip(tgts, pol.policy_nets):
+            t.load_state_dict(n.state_dict()); t.eval()
+        sgd = lambda n: torch.optim.SGD(n.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)   # noqa: E731
+        opts, opts_i = [sgd(n) for n in pol.policy_nets], [sgd(n) for n in pol.intention_nets]
+        batches = [synth.synth_batch(B, C, A, 70 + i, terminal_every=4) for i, A in enumerate((2, 1))]
+        if grouped:
+            info = T.train_groups(cfg, pol, tgts, opts, batches, opts_i)
+        else:
+            info = {}
+            for i in range(2):
+                r = T.train(cfg, pol.policy_nets[i], tgts[i], opts[i], batches[i], pol.apply_transform, cfg.discount_factors[i])
+                r.update(T.train_intention(pol.intention_nets[i], opts_i[i], batches[i], pol.apply_transform))
+                info.update({'{}/robot_group_{:02}'.format(k, i + 1): v for k, v in r.items()})
+        outs.append((info, [n.module.flat_params.clone() for n in pol.policy_nets + pol.intention_nets]))
+        if grouped:
+            assert sorted(info) == sorted(f'{k}/robot_group_{g:02}' for k in ('loss', 'td_error', 'loss_intention') for g in (1, 2))
+            for i in range(2):
+                ref = O.dqn_step(O.clone_state(states[i]), O.clone_state(states[i]), None, *G.batch_tensors(batches[i]), discount=0.85)
+                tag = f'robot_group_{i + 1:02}'
+                assert abs(info[f'loss/{tag}'] - float(ref['loss'])) <= 1e-3 * abs(float(ref['loss'])), (i, info, float(ref['loss']))
+                assert abs(info[f'td_error/{tag}'] - float(ref['td_error'])) <= 1e-3 * abs(float(ref['td_error']))
+                refi = O.intention_step(O.clone_state(states[2 + i]), None, list(batches[i].state))
+                assert abs(info[f'loss_intention/{tag}'] - refi['loss_intention']) <= 1e-3 * abs(refi['loss_intention'])
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_bf16_mode_is_characterised_and_not_default():
     """simq_set_precision(BF16) -- one MMA per product -- is opt-in: its Q-map error is of the order SURVEY.md
     §7.2-1 predicts for bf16 operands (1e-2: outside the 1e-3 parity bar), the default mode is untouched by it."""
