@@ -387,7 +387,7 @@ def run_simq(args):
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': hb.h2d_bytes(), 'd2h_bytes_per_step': 8,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': 'conv2_umma_kernel / conv_umma_kernel (tcgen05 conv + dgrad, all launches of the step)', 'achieved': conv_tf, 'peak': sustained / 1.0,
+            'roofline': {'bound': 'tensor', 'kernel': 'conv2w_umma_kernel / conv2_umma_kernel / conv_umma_kernel (tcgen05 conv + dgrad, all launches of the step)', 'achieved': conv_tf, 'peak': sustained / 1.0,
                          'unit': 'TFLOP/s', 'frac': conv_tf / sustained, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': f'{how} bf16 sustained',
                          'launches': int(pl[0]), 'ms_per_step_in_kernel': pm[0] / args.steps,
                          'share_of_step': (pm[0] / args.steps) / (ms_prof / args.steps), 'ms_per_step_profiled_pass': ms_prof / args.steps,

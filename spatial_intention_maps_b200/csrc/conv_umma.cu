@@ -572,6 +572,189 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Windowed CTA-pair variant for the 3x3 convs: the 9 taps of a pitch-25 conv read the SAME activation rows shifted by
+// -26..+26, so instead of re-loading the 128 A rows of a tile for every tap (9 x 32 KB per 64-wide K chunk) each CTA
+// stages ONE window of 184 rows per K chunk -- tile rows -26..+157 -- and the MMA of tap t reads it through a shared
+// memory descriptor whose start address is advanced by (26 + off_t) rows of 128 bytes.  SWIZZLE_128B permutes the
+// 16-byte chunks of a row by (row mod 8), both in what TMA writes and in what the MMA reads, as a function of the
+// absolute shared-memory address bits [7,10): a descriptor whose start address is advanced by whole rows therefore stays
+// consistent with what TMA wrote, with the base-offset field left at 0 (measured: setting it to (addr >> 7) & 7 breaks
+// the result, leaving it 0 is exact for all 9 row shifts).  The loop order becomes K chunk outer, tap inner; W tiles stream
+// through their own ring.  L2 -> shared traffic per tensor cycle drops from 64 KB to 32 + 47/9 = 37 KB per stage
+// (-42 %): the step is power-bound, fewer bytes moved per MMA = more clock for the MMAs.
+// (The same scheme for the single-CTA 128 x 64/128 tiles of stages 1-2 was built and measured: no gain -- those launches
+// are bound by their epilogues and fixed costs, not by the A loads -- and dropped.)
+// ------------------------------------------------------------------------------------------------
+
+#define WIN_LEAD 26                                           // PITCH + 1: window row of tile row 0 at tap offset 0
+#define WIN_ROWS 184                                          // 128 + 2 * 26 = 180, rounded up to the 8-row swizzle atom
+
+template <int TERMS>
+struct Conv2WCfg {
+    static constexpr int BN = 256;
+    static constexpr int A_BYTES = WIN_ROWS * UM_BK * 2;      // one plane of this CTA's window (23 KB)
+    static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of one W tile, one plane (16 KB)
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int A_BUFS = 2;
+    static constexpr int A_BUF_BYTES = PLANES * A_BYTES;
+    static constexpr int W_STAGE_BYTES = PLANES * W_BYTES;
+    static constexpr int W_STAGES = TERMS == 3 ? 3 : 6;
+    static constexpr int W_BASE = A_BUFS * A_BUF_BYTES;
+    static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
+    static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
+    static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = RING_BYTES + FIXED;
+    static constexpr int TMEM_COLS = 512;
+};
+
+template <int FL, int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
+conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                   const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
+                   int N, int m2_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
+    using Cfg = Conv2WCfg<TERMS>;
+    constexpr int BN = Cfg::BN;
+    static_assert(Cfg::A_BYTES % 1024 == 0, "window planes must keep the 1024-byte swizzle alignment");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    float* staging = reinterpret_cast<float*>(base_ptr + Cfg::RING_BYTES);
+    float* csum = reinterpret_cast<float*>(base_ptr + Cfg::RING_BYTES + Cfg::STAGING_BYTES);
+    const uint32_t bars = base + Cfg::RING_BYTES + Cfg::STAGING_BYTES + Cfg::CSUM_BYTES;
+    auto afull_bar = [&](int b) { return bars + 8u * b; };
+    auto aempty_bar = [&](int b) { return bars + 8u * (2 + b); };
+    auto wfull_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto wempty_bar = [&](int s) { return bars + 8u * (4 + Cfg::W_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (4 + 2 * Cfg::W_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (6 + 2 * Cfg::W_STAGES + a); };
+    const uint32_t tmem_slot = bars + 8u * (8 + 2 * Cfg::W_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int kchunks = K / UM_BK;
+    const int total_tiles = m2_tiles * n_tiles;
+    // this pair's tiles: cluster_id, cluster_id + num_clusters, ...; a "step" g = one (tile, K chunk) = one A window
+    const int my_tiles = cluster_id < total_tiles ? (total_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const int steps = my_tiles * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), 1); }
+        for (int s = 0; s < Cfg::W_STAGES; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mAhi); tma_prefetch_desc(&mAlo); tma_prefetch_desc(&mWhi); tma_prefetch_desc(&mWlo);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the window of step g: rows m0 - 26 .. m0 + 157 of K chunk kc (rows outside the tensor are zero-filled)
+            auto load_window = [&](int g) {
+                const int tile = cluster_id + (g / kchunks) * num_clusters, kc = g % kchunks;
+                const int m0 = (tile / n_tiles) * 256 + (int)rank * UM_BM;
+                const int b = g & 1;
+                mbar_wait(aempty_bar(b), ((uint32_t)(g >> 1) & 1u) ^ 1u);
+                if (rank == 0) mbar_expect_tx(afull_bar(b), 2 * Cfg::A_BUF_BYTES);
+                const uint32_t fb = mapa_rank0(afull_bar(b));
+                const uint32_t sa = base + b * Cfg::A_BUF_BYTES;
+                tma_load_2d_cg2(sa, &mAhi, fb, kc * UM_BK, m0 - WIN_LEAD);
+                if (TERMS == 3) tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 - WIN_LEAD);
+            };
+            int s = 0; uint32_t ph = 0;
+            if (steps > 0) load_window(0);
+            for (int g = 0; g < steps; ++g) {
+                const int tile = cluster_id + (g / kchunks) * num_clusters, kc = g % kchunks;
+                const int n0 = (tile % n_tiles) * BN;
+                const int wn0 = n0 + (int)rank * (BN / 2);
+                for (int t = 0; t < 9; ++t) {
+                    if (t == 3 && g + 1 < steps) load_window(g + 1);        // prefetch: its buffer was freed a full step ago
+                    mbar_wait(wempty_bar(s), ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(wfull_bar(s), 2 * Cfg::W_STAGE_BYTES);
+                    const uint32_t fb = mapa_rank0(wfull_bar(s));
+                    const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
+                    tma_load_2d_cg2(sw, &mWhi, fb, kc * UM_BK, t * N + wn0);
+                    if (TERMS == 3) tma_load_2d_cg2(sw + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
+                    if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc(256, BN, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t aph = 0;
+            for (int g = 0; g < steps; ++g) {
+                const int kc = g % kchunks;
+                if (kc == 0) {
+                    mbar_wait(tempty_bar(acc), aph ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const int b = g & 1;
+                mbar_wait(afull_bar(b), (uint32_t)(g >> 1) & 1u);
+                const uint32_t sa = base + b * Cfg::A_BUF_BYTES;
+                for (int t = 0; t < 9; ++t) {
+                    const int off = (t / 3 - 1) * PITCH + (t % 3 - 1);
+                    const uint32_t arow = sa + (uint32_t)(WIN_LEAD + off) * 128u;
+                    mbar_wait(wfull_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t a_hi = umma_desc(arow + k * 32, 16, 1024);
+                        const uint64_t w_hi = umma_desc(sw + k * 32, 16, 1024);
+                        const uint32_t accumulate = (kc | t | k) != 0;
+                        if (TERMS == 3) {
+                            const uint64_t a_lo = umma_desc(arow + Cfg::A_BYTES + k * 32, 16, 1024);
+                            const uint64_t w_lo = umma_desc(sw + Cfg::W_BYTES + k * 32, 16, 1024);
+                            tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, accumulate);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else {
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, accumulate);
+                        }
+                    }
+                    tc_commit_mc2(wempty_bar(s));
+                    if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
+                }
+                tc_commit_mc2(aempty_bar(b));                    // the window is free once the 9 taps have read it
+                if (kc == kchunks - 1) {
+                    tc_commit_mc2(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; aph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+            const int m2 = tile / n_tiles, n0 = (tile - m2 * n_tiles) * BN;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            epilogue_tile<BN, FL, true>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m2 * 2 + (int)rank, n0, rows, N,
+                                        out, ep, quad, lane);
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad: partial[z][co][ci] = sum_{p in split} dY[p][co] * X[p + off_t][ci],  z = split*ntaps + t
 // ------------------------------------------------------------------------------------------------
 template <int BN, int TERMS = 3>
@@ -966,6 +1149,38 @@ static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int nta
     return 0;
 }
 
+// windowed pair kernel (3x3 convs only): the A maps carry a 184-row box
+static int conv_window_mode() {      // SIMQ_CONV_WINDOW=0 falls back to the per-tap A loads (A/B experiments)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW"); mode = e ? atoi(e) : 1; }
+    return mode;
+}
+template <int FL, int TERMS>
+static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float* out, ConvEpilogue ep, cudaStream_t s) {
+    using Cfg = Conv2WCfg<TERMS>;
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2w_umma_kernel<FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (!g_num_sms) {
+        int dev = 0;
+        SIMQ_CUDA(cudaGetDevice(&dev));
+        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap mAhi, mAlo, mWhi, mWlo;
+    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, WIN_ROWS) || make_map(&mAlo, A.t.lo, A.rows, A.cols, WIN_ROWS) ||
+        make_map(&mWhi, W.t.hi, W.rows, W.cols, Cfg::BN / 2) || make_map(&mWlo, W.t.lo, W.rows, W.cols, Cfg::BN / 2))
+        return 1;
+    const int m2_tiles = ceil_div(A.rows, 256), n_tiles = N / Cfg::BN;
+    int clusters = g_num_sms / 2;
+    if (m2_tiles * n_tiles < clusters) clusters = m2_tiles * n_tiles;
+    const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * 9, s);
+    conv2w_umma_kernel<FL, TERMS><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, m2_tiles, n_tiles,
+                                                                         out, ep);
+    prof_mark(PROF_CONV, false, 0, s);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 // the epilogue variants the network uses
 template <int BN, bool PAIR = false>
 static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
@@ -981,8 +1196,13 @@ static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     if (ep.bn_raw) fl |= EF_BNBWD;
     switch (fl) {
 #define CASE(F) case (F):                                                                                                   \
-        if (ep.terms == 1) return PAIR ? launch_conv2<(F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 1>(A, W, N, ntaps, out, ep, s); \
-        return PAIR ? launch_conv2<(F), 3>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 3>(A, W, N, ntaps, out, ep, s)
+        if constexpr (PAIR) {                                                                                               \
+            if (ntaps == 9 && conv_window_mode() != 0)                                                                      \
+                return ep.terms == 1 ? launch_conv2w<(F), 1>(A, W, N, out, ep, s) : launch_conv2w<(F), 3>(A, W, N, out, ep, s); \
+            return ep.terms == 1 ? launch_conv2<(F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv2<(F), 3>(A, W, N, ntaps, out, ep, s); \
+        } else {                                                                                                            \
+            return ep.terms == 1 ? launch_conv<BN, (F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 3>(A, W, N, ntaps, out, ep, s); \
+        }
         CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
         CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
         CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
