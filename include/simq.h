@@ -108,6 +108,12 @@ int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const flo
                     const float* reward, const uint8_t* nonfinal, int B, int Bn, float gamma, float lr,
                     float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
                     float* out2, simq_stream stream);
+/* Optional, one-shot: `event` (a cudaEvent_t the caller records after the host->device copy of s_next, e.g. on a copy
+ * stream) is what the NEXT simq_train_step waits for before anything reads s_next -- on the lane that runs the s'
+ * passes only, so the copy of s' overlaps the forward on s (the reference uploads s' with non_blocking=True for the same
+ * reason, train.py:112).  Inside a captured step the wait is an external event-wait node; the handle is part of the graph
+ * key.  NULL clears it. */
+int simq_set_next_state_event(simq_ctx*, void* event);
 
 /* Replay-batch assembly on the device (replaces the per-sample transform + torch.cat + H2D of
  * train.py:109-112 when the replay buffer is device-resident): dst[j][:] = src[idx[j]][:], rows of

@@ -148,6 +148,7 @@ struct simq_ctx {
     float *partials2, *wscratch2; Split dyA2; double* bn_defer;
     cudaStream_t aux_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[4];
     int lanes_mode;                  // -1: read SIMQ_LANES on first use; 0 serial schedule; 1 two lanes
+    cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     long long launches0;
     // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
@@ -309,7 +310,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
         }
     }
     c->launches0 = g_simq_launches;
-    c->aux_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1;
+    c->aux_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1; c->next_ready = nullptr;
     for (auto& e : c->ev_pool) e = nullptr;
     for (auto& e : c->ev_done) e = nullptr;
     c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0; c->graph_misses = 0;
@@ -771,7 +772,7 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
                            const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
                            const float* s_next, int x_layout, const int64_t* action, const float* reward,
                            const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
-                           int first_step, int double_dqn, int apply_update, float* out2, cudaStream_t s) {
+                           int first_step, int double_dqn, int apply_update, float* out2, cudaEvent_t next_ready, cudaStream_t s) {
     int err;
     PackedSet* pw = get_packed(c, params, 0, s, &err);                                     // SGD changed them last step
     if (err) return 1;
@@ -796,6 +797,13 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
     if (Bn > 0) {
         // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again: after the
         // s pass's update, so a concurrent s' pass stashes its batch statistics and they are applied after the join)
+        if (next_ready) {
+            // the caller uploads s' on a copy stream while the s pass already runs: only the s' lane waits for it.  The event
+            // belongs to the caller (recorded outside any capture): inside a captured step it becomes an external event-wait node
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            SIMQ_CUDA(cudaStreamIsCapturing(LB.s, &cap));
+            SIMQ_CUDA(cudaStreamWaitEvent(LB.s, next_ready, cap == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
+        }
         if (two) LB.defer = c->bn_defer;
         if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, LB));
         LB.defer = nullptr;
@@ -923,17 +931,25 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
                                  (uint64_t)target_hit, (uint64_t)grads, (uint64_t)momentum, (uint64_t)s_, (uint64_t)s_next, (uint64_t)x_layout,
                                  (uint64_t)action, (uint64_t)reward, (uint64_t)nonfinal, (uint64_t)B, (uint64_t)Bn, fbits(gamma), fbits(lr),
                                  fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step, (uint64_t)double_dqn, (uint64_t)apply_update,
-                                 (uint64_t)out2};
+                                 (uint64_t)out2, (uint64_t)c->next_ready};
+    cudaEvent_t next_ready = c->next_ready;
+    c->next_ready = nullptr;                                    // one-shot
     return run_graphed(c, key, (cudaStream_t)stream,
         [&](cudaStream_t st) {
             return train_step_body(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout,
                                    action, reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update,
-                                   out2, st);
+                                   out2, next_ready, st);
         },
         [&]() {
             if (Bn > 0) packed_set_version(c, target_params, target_version);
             c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1;
         });
+}
+
+extern "C" int simq_set_next_state_event(simq_ctx* c, void* event) {
+    if (!c) { simq_set_error("simq_set_next_state_event: ctx is NULL"); return 1; }
+    c->next_ready = (cudaEvent_t)event;
+    return 0;
 }
 
 extern "C" int simq_gather_rows(const float* src, const int64_t* idx, int n, int64_t row_floats, float* dst, simq_stream stream) {

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from collections import namedtuple
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -97,14 +99,29 @@ class DeviceBatch:
         self.out2 = torch.zeros(2, dtype=torch.float32, device=device)
         self.out2_host = torch.zeros(2, dtype=torch.float32, pin_memory=torch.cuda.is_available())
         self.Bn = 0
+        self.ns_ready = None                     # event of a pending s' upload on the copy stream (consumed by the next step)
+        self._copy_stream = self._ev_s = self._ev_ns = None
 
     def upload(self, hb: HostBatch):
+        """Host -> device on the current stream, except the next states: they go second over the same link on a copy
+        stream, and only the s' lane of the step waits for them (``simq_set_next_state_event``), so their half of the
+        transfer runs under the forward on s."""
+        cur = torch.cuda.current_stream(self.s.device)
         self.s.copy_(hb.s, non_blocking=True)
-        if hb.Bn:
-            self.ns[:hb.Bn].copy_(hb.ns[:hb.Bn], non_blocking=True)
         self.action.copy_(hb.action, non_blocking=True)
         self.reward.copy_(hb.reward, non_blocking=True)
         self.nonfinal.copy_(hb.nonfinal, non_blocking=True)
+        self.ns_ready = None
+        if hb.Bn:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.s.device)
+                self._ev_s, self._ev_ns = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_s.record(cur)               # after s (the link is shared: s first) and after every earlier reader of self.ns
+            self._copy_stream.wait_event(self._ev_s)
+            with torch.cuda.stream(self._copy_stream):
+                self.ns[:hb.Bn].copy_(hb.ns[:hb.Bn], non_blocking=True)
+                self._ev_ns.record(self._copy_stream)
+            self.ns_ready = self._ev_ns
         self.Bn = hb.Bn
         return self
 
@@ -167,6 +184,9 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
     lr, mom, wd = float(g['lr']), float(g.get('momentum', 0.0)), float(g.get('weight_decay', 0.0))
     grads = policy.flat_grad()
     L = _lib.lib()
+    ns_ready, db.ns_ready = getattr(db, 'ns_ready', None), None
+    if ns_ready is not None:                 # s' is still on its way on the copy stream (DeviceBatch.upload)
+        _lib.check(L.simq_set_next_state_event(ctx.handle, C.c_void_p(ns_ready.cuda_event)), 'simq_set_next_state_event')
     _lib.check(L.simq_train_step(
         ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(policy.flat_bn), _lib.ptr(policy.flat_nbt),
         _lib.ptr(target.flat_params), _lib.ptr(target.flat_bn), target.params_version, _lib.ptr(grads),
