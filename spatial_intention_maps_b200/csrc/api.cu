@@ -142,7 +142,7 @@ struct simq_ctx {
     float* partials; float* sums; double* dpartials;
     BnEntry* bn_table;               // device table of the 22 BatchNorms (one-launch eval affine)
     float *G[2], *g_mid, *du1, *dt, *dz0, *dy0, *hp, *wscratch, *stem_partials;
-    Split dyA, dyB, dy2h, dy0s; float* stem_tmp;
+    Split dyA, dyB, dy2h, dy0s; float *stem_tmp, *h2_tmp;
     // second lane (see "lanes" below): its own column-sum partials and split-K / wgrad scratch, the ping-pong partner of
     // dyA, and the stash of the deferred running-statistics update of the s' pass
     float *partials2, *wscratch2; Split dyA2; double* bn_defer;
@@ -215,7 +215,7 @@ static void carve_all(simq_ctx* c, bool dry) {
         for (size_t i = 0; i < convs.size(); ++i) {
             size_t n = (size_t)convs[i].cout * convs[i].cin * convs[i].k * convs[i].k;
             c->packed[p].fwd[i] = carve_split(c, n, dry);
-            c->packed[p].bwd[i] = carve_split(c, n, dry);
+            c->packed[p].bwd[i] = carve_split(c, convs[i].cout < 64 ? n / convs[i].cout * 64 : n, dry);   // dgrad K padded to 64 (head conv2)
         }
         c->packed[p].stem = carve_split(c, (size_t)64 * stem_kp(d.C), dry);
         c->packed[p].table = carve<PackEntry>(c, 32, dry);
@@ -248,7 +248,8 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->dyA = carve_split(c, R25 * 512, dry);
     c->dyA2 = carve_split(c, R25 * 512, dry);
     c->dyB = carve_split(c, R25 * 512, dry);
-    c->dy2h = carve_split(c, R48 * 32, dry);
+    c->dy2h = carve_split(c, R48 * HEAD2_DY_STRIDE, dry);
+    c->h2_tmp = carve<float>(c, (size_t)HEAD2_DY_STRIDE * 128, dry);
     c->dy0s = carve_split(c, R48 * 64, dry);
     c->stem_tmp = carve<float>(c, (size_t)64 * stem_kp(d.C), dry);
     c->q_s = carve<float>(c, B * 2 * 9216, dry);
@@ -300,7 +301,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
             long long start = 0;
             for (size_t i = 0; i < convs.size(); ++i) {
                 PackEntry& E = host[i];
-                E.start = start; E.w_off = c->d.poff[convs[i].w]; E.cout = convs[i].cout; E.cin = convs[i].cin; E.kk = convs[i].k * convs[i].k; E.pad = 0;
+                E.start = start; E.w_off = c->d.poff[convs[i].w]; E.cout = convs[i].cout; E.cin = convs[i].cin; E.kk = convs[i].k * convs[i].k; E.bk = convs[i].cout < 64 ? 64 : 0;
                 E.fhi = c->packed[p].fwd[i].hi; E.flo = c->packed[p].fwd[i].lo; E.bhi = c->packed[p].bwd[i].hi; E.blo = c->packed[p].bwd[i].lo;
                 start += (long long)E.cout * E.cin * E.kk;
             }
@@ -648,10 +649,14 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                         grads + d.poff[d.h3_bias], s));
     TRY(k_head2_apply(c->dt, S.raw_h2, R48, A, bnstat(S, hb2, BS_SCALE), bnstat(S, hb2, BS_SHIFT), bnstat(S, hb2, BS_MEAN),
                       bnstat(S, hb2, BS_INVSTD), params + d.poff[d.h3.w], c->sums, cnt48, c->dy2h, s));
-    TRY(wgrad_on_w(BUF_MISC, c->dy2h, S.u1, R48, 32, 128, 1, grads + d.poff[d.h2.w]));
-    TRY(bias_grad(c, c->dy2h, R48, 32, grads + d.poff[d.h2_bias], M));
+    // head conv2 has 32 output channels: its dy is stored 64 wide (upper half zero), so dW comes out as [64][128] with rows
+    // 32..63 zero (the first 32 rows are the gradient) and the dgrad contracts over a zero-padded K of 64
+    TRY(wgrad_on_w(BUF_MISC, c->dy2h, S.u1, R48, HEAD2_DY_STRIDE, 128, 1, c->h2_tmp));
+    SIMQ_CUDA(cudaMemcpyAsync(grads + d.poff[d.h2.w], c->h2_tmp, sizeof(float) * 32 * 128, cudaMemcpyDeviceToDevice, ws));
+    TRY(bias_grad(c, c->dy2h, R48, HEAD2_DY_STRIDE, c->sums, M));
+    SIMQ_CUDA(cudaMemcpyAsync(grads + d.poff[d.h2_bias], c->sums, sizeof(float) * 32, cudaMemcpyDeviceToDevice, s));
     ConvEpilogue ep0 = conv_ep(0);
-    TRY(conv_any(c, be, c->dy2h, R48, 32, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M));
+    TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     float* G = c->G[0];
     float* Gn = c->G[1];

@@ -209,6 +209,28 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
         float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (FL & EF_AFFINE) { sc4 = *reinterpret_cast<const float4*>(ep.scale + n); sh4 = *reinterpret_cast<const float4*>(ep.shift + n); }
         const size_t o0 = (size_t)(mw + sr) * N + n;
+        // global operands of the transforms, all 8 row groups up front: issued back to back, their latencies overlap (inside
+        // the store loop every load would wait behind the previous group's store -- add_prev may alias out -- and the
+        // epilogue of a short-K launch becomes a chain of ~64 dependent DRAM round trips per tile)
+        float4 pv[8], gv[8];
+        uint2 rh[8], rl[8], gm[8];
+        if (FL & (EF_PREV | EF_RES | EF_G)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + sr;
+                const size_t o = o0 + (size_t)(i * 4) * N;
+                const bool live = mw + r < rows && ((vmask >> r) & 1u);
+                if (FL & EF_PREV) pv[i] = live ? *reinterpret_cast<const float4*>(ep.add_prev + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FL & EF_RES) {
+                    rh[i] = live ? *reinterpret_cast<const uint2*>(ep.res.hi + o) : make_uint2(0u, 0u);
+                    rl[i] = live ? *reinterpret_cast<const uint2*>(ep.res.lo + o) : make_uint2(0u, 0u);
+                }
+                if (FL & EF_G) {
+                    gv[i] = live ? *reinterpret_cast<const float4*>(ep.add_g + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gm[i] = live ? *reinterpret_cast<const uint2*>(ep.add_g_mask + o) : make_uint2(0u, 0u);
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + sr;
@@ -217,17 +239,15 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
             const size_t o = o0 + (size_t)(i * 4) * N;
             if ((vmask >> r) & 1u) {
                 if (FL & EF_AFFINE) { x.x = fmaf(x.x, sc4.x, sh4.x); x.y = fmaf(x.y, sc4.y, sh4.y); x.z = fmaf(x.z, sc4.z, sh4.z); x.w = fmaf(x.w, sc4.w, sh4.w); }
-                if (FL & EF_PREV) { float4 p = *reinterpret_cast<const float4*>(ep.add_prev + o); x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
+                if (FL & EF_PREV) { const float4 p = pv[i]; x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w; }
                 if (FL & EF_RES) {
-                    uint2 h = *reinterpret_cast<const uint2*>(ep.res.hi + o), l = *reinterpret_cast<const uint2*>(ep.res.lo + o);
-                    const bf16* hb = reinterpret_cast<const bf16*>(&h); const bf16* lb = reinterpret_cast<const bf16*>(&l);
+                    const bf16* hb = reinterpret_cast<const bf16*>(&rh[i]); const bf16* lb = reinterpret_cast<const bf16*>(&rl[i]);
                     x.x += bf2f(hb[0]) + bf2f(lb[0]); x.y += bf2f(hb[1]) + bf2f(lb[1]);
                     x.z += bf2f(hb[2]) + bf2f(lb[2]); x.w += bf2f(hb[3]) + bf2f(lb[3]);
                 }
                 if (FL & EF_G) {
-                    float4 g = *reinterpret_cast<const float4*>(ep.add_g + o);
-                    uint2 mk = *reinterpret_cast<const uint2*>(ep.add_g_mask + o);
-                    const bf16* mb = reinterpret_cast<const bf16*>(&mk);
+                    const float4 g = gv[i];
+                    const bf16* mb = reinterpret_cast<const bf16*>(&gm[i]);
                     if (bf2f(mb[0]) > 0.f) x.x += g.x;
                     if (bf2f(mb[1]) > 0.f) x.y += g.y;
                     if (bf2f(mb[2]) > 0.f) x.z += g.z;

@@ -42,7 +42,7 @@ int k_sgd_step(float* params, float* grads, float* momentum, long long n, float 
 // fwd: n = cout, k = cin.   bwd (dgrad): n = cin, k = cout, taps flipped.
 int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split bwd, cudaStream_t s);
 // all convs of a network in ONE launch: table entry = one conv (elements [start, start + cout*cin*kk) of the launch)
-struct PackEntry { long long start; long long w_off; int cout, cin, kk, pad; bf16 *fhi, *flo, *bhi, *blo; };
+struct PackEntry { long long start; long long w_off; int cout, cin, kk, bk /* dgrad K stride, 0 = cout */; bf16 *fhi, *flo, *bhi, *blo; };
 int k_pack_all(const float* params, const PackEntry* table_dev, int n, long long total, cudaStream_t s);
 
 // ---- backward elementwise ----
@@ -52,6 +52,7 @@ int k_head2_reduce(const float* dt, const float* raw_h2, long long rows, int A, 
                    const float* shift, const float* mean, const float* invstd, const float* w3, float* partials,
                    cudaStream_t s);
 int k_reduce_partials(const float* partials, int nblk, int K, float* out, float mul, cudaStream_t s);
+#define HEAD2_DY_STRIDE 64          // dy of head conv2: 32 channels zero-padded to the tensor-core tile
 int k_head2_apply(const float* dt, const float* raw_h2, long long rows, int A, const float* scale, const float* shift,
                   const float* mean, const float* invstd, const float* w3, const float* sums, double count,
                   Split dy, cudaStream_t s);

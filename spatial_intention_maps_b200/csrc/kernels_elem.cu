@@ -628,7 +628,9 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__
     {   // dgrad pack: [t][ci][co] with the taps rotated by 180 degrees
         int co = (int)(idx % cout), ci = (int)((idx / cout) % cin), t = (int)(idx / ((long long)cin * cout));
         float v = w[((size_t)co * cin + ci) * kk + (kk - 1 - t)];
-        split_store(v, E.bhi[idx], E.blo[idx]);
+        // bk > cout: the contraction dim of the dgrad GEMM is zero-padded to bk (the padding is never written: the pool is zero-filled)
+        const size_t o = E.bk > cout ? ((size_t)t * cin + ci) * E.bk + co : (size_t)idx;
+        split_store(v, E.bhi[o], E.blo[o]);
     }
 }
 
@@ -812,7 +814,11 @@ __global__ void __launch_bounds__(256) head2_apply_kernel(const float* __restric
     float d0 = dt[(size_t)p * A], d1 = A > 1 ? dt[(size_t)p * A + 1] : 0.f;
     float dz = h > 0.f ? (w3[lane] * d0 + (A > 1 ? w3[32 + lane] * d1 : 0.f)) : 0.f;
     float v = sc * (dz - c1 - xh * c2);
-    split_store(v, dy.hi[(size_t)p * 32 + lane], dy.lo[(size_t)p * 32 + lane]);
+    // dy rows are HEAD2_DY_STRIDE = 64 wide, channels 32..63 zero: the 32-channel conv2 then runs its dgrad / wgrad on the
+    // tensor-core tiles (K resp. M of 64) instead of the FMA comparator kernels
+    const size_t o = (size_t)p * HEAD2_DY_STRIDE + lane;
+    split_store(v, dy.hi[o], dy.lo[o]);
+    dy.hi[o + 32] = __float2bfloat16_rn(0.f); dy.lo[o + 32] = __float2bfloat16_rn(0.f);
 }
 
 int k_head2_apply(const float* dt, const float* raw_h2, long long rows, int A, const float* scale, const float* shift,
