@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsimq.so')
+LIB_PATH = os.environ.get('SIMQ_LIB_PATH') or os.path.join(_HERE, 'libsimq.so')      # override: A/B of two builds in one session
 
 BACKEND_UMMA, BACKEND_FMA = 0, 1
 PRECISION_PARITY, PRECISION_BF16 = 0, 1
