@@ -137,8 +137,13 @@ def shard_batch(batch, rank: int, world: int):
 
 
 def allreduce_mean_(grads: torch.Tensor, out2: torch.Tensor, world: int):
-    """The path's one exchange: sum the flat fp32 gradient vector (and the 2-float loss / td_error
-    report) over ranks, divide by the world size -> gradient of the global-batch mean loss."""
+    """The path's one exchange: average the flat fp32 gradient vector (and the 2-float loss / td_error report) over
+    ranks -> gradient of the global-batch mean loss.  NCCL averages inside the collective (no extra pass over the
+    45 MB vector); back-ends without AVG (gloo, used by the CPU tests) sum and scale."""
+    if dist.get_backend() == 'nccl':
+        dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+        dist.all_reduce(out2, op=dist.ReduceOp.AVG)
+        return
     dist.all_reduce(grads)
     grads.mul_(1.0 / world)
     dist.all_reduce(out2)
@@ -208,6 +213,7 @@ def _enqueue_train(cfg, policy_net, target_net, optimizer, batch, discount_facto
     B = int(cfg.batch_size)
     C = policy.num_input_channels
     dev = policy.flat_params.device
+    policy.ctx(B)                                # fails loudly (SimqError) off a B200: there is no CPU path
     cache = policy.__dict__.setdefault('_batch_cache', {})
     if cache.get('key') != (B, C, dev):
         cache.clear()

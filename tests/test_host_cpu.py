@@ -107,6 +107,30 @@ def test_policy_surface():
     assert torch.equal(tgt[0].module.flat_params, pol.policy_nets[0].module.flat_params)
 
 
+def test_train_groups_checks_its_arguments_and_has_no_cpu_path():
+    """train.train_groups (the training block of train.py:253-263): one target net / optimizer / batch per robot group,
+    intention optimizers when cfg.use_predicted_intention; on a CPU-resident policy the first update raises (no fallback)."""
+    class Cfg:
+        robot_config = [{'lifting_robot': 2}, {'pushing_robot': 2}]
+        num_input_channels, batch_size, final_exploration = 5, 4, 0.01
+        checkpoint_path = policy_path = None
+        discount_factors = [0.85, 0.85]
+        use_predicted_intention = True
+        use_double_dqn, grad_norm_clipping = True, 100
+    cfg = Cfg()
+    pol = policies.DQNIntentionPolicy(cfg, train=True, device='cpu')
+    tgts = pol.build_policy_nets()
+    opts = [torch.optim.SGD(n.parameters(), lr=0.01, momentum=0.9) for n in pol.policy_nets]
+    batches = [synth.synth_batch(4, 5, A, 3 + A, terminal_every=2) for A in (2, 1)]
+    with pytest.raises(ValueError):
+        T.train_groups(cfg, pol, tgts[:1], opts, batches)
+    with pytest.raises(ValueError):
+        T.train_groups(cfg, pol, tgts, opts, batches)             # intention optimizers missing
+    opts_i = [torch.optim.SGD(n.parameters(), lr=0.01, momentum=0.9) for n in pol.intention_nets]
+    with pytest.raises(_lib.SimqError):
+        T.train_groups(cfg, pol, tgts, opts, batches, opts_i)
+
+
 def test_host_batch_compacts_next_states_like_the_reference():
     batch = synth.synth_batch(8, 4, 2, 5, terminal_every=4)
     hb = T.HostBatch(8, 4).fill(batch)
