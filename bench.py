@@ -213,8 +213,11 @@ def run_simq(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: NCCL's own output (version banner, warnings) goes to stderr.  NCCL honours
+        # NCCL_DEBUG_FILE only above the VERSION level, and prints its banner at VERSION and WARN
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     B = args.batch
