@@ -282,6 +282,18 @@ def run_simq(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     loss = float(db.out2_host[0])
+    # ---- informational: the literal user call train.train(cfg, ..., batch of numpy arrays, ...) incl. host staging ----
+    import types
+    cfg = types.SimpleNamespace(batch_size=B, grad_norm_clipping=100, use_double_dqn=True)
+
+    def train_call():
+        T.train(cfg, pol, tgt, opt, batch, None, GAMMA)
+    train_call()
+    t0 = time.perf_counter()
+    ncall = max(2, args.steps // 2)
+    for _ in range(ncall):
+        train_call()
+    ms_call = (time.perf_counter() - t0) * 1e3 / ncall
     # ---- informational: the same step under the serial schedule (one stream; simq_set_schedule) ----
     serial = None
     if not args.no_serial:
@@ -406,6 +418,9 @@ def run_simq(args):
             'fwd_bwd_only': {'value': world * B / (ms_fb * 1e-3), 'unit': UNIT, 'ms': ms_fb},
             'forward_only': {'value': world * B / (ms_f * 1e-3), 'unit': UNIT, 'ms': ms_f, 'note': 'train-mode BN, no_grad'},
             'serial_schedule': serial, 'c_star': cstar,
+            'train_call': {'ms_per_call': ms_call, 'value': world * B / (ms_call * 1e-3), 'unit': UNIT,
+                           'note': 'wall clock of train.train(cfg, policy_net, target_net, optimizer, Transition of numpy arrays, ...) on rank 0: '
+                                   'threaded staging into pinned memory (the upload of s starts while s\' is still being staged) + e2e step + sync'},
             'clocks': clocks, 'loss': loss, 'bf16_fast_mode': fast, 'torch_cudnn_same_gpu': torch_gpu,
         }
         if world == 1 and not args.no_cpu:

@@ -54,9 +54,11 @@ class HostBatch:
 
     _pool = None
 
-    def fill(self, batch):
+    def fill(self, batch, after_states=None):
         """Stage one ``Transition`` of tuples.  The 2*B row copies (184 KB each at C=5) are spread over a few threads
-        (numpy releases the GIL while copying): ~4x faster than the serial loop at B=128."""
+        (numpy releases the GIL while copying): ~4x faster than the serial loop at B=128.  States and the small vectors
+        are staged first; ``after_states()`` (if given) runs before the next states are staged, so the caller can start
+        the host->device copy of s while this thread is still copying s' (``_enqueue_train``)."""
         B = self.B
         if len(batch.state) != B:
             raise ValueError(f'batch has {len(batch.state)} transitions, expected {B}')
@@ -64,25 +66,35 @@ class HostBatch:
         nf = np.fromiter((n is not None for n in batch.next_state), dtype=bool, count=B)
         slot = np.cumsum(nf) - 1                     # row of sample i in the compacted next-state batch (train.py:112)
 
-        def copy_rows(lo, hi):
+        def copy_states(lo, hi):
             for i in range(lo, hi):
                 s_np[i] = batch.state[i]
+
+        def copy_next(lo, hi):
+            for i in range(lo, hi):
                 if nf[i]:
                     ns_np[slot[i]] = batch.next_state[i]
 
         workers = min(8, max(1, B // 16))
-        if workers == 1:
-            copy_rows(0, B)
-        else:
-            if HostBatch._pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-                HostBatch._pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix='simq-stage')
-            step = (B + workers - 1) // workers
-            list(HostBatch._pool.map(lambda lo: copy_rows(lo, min(B, lo + step)), range(0, B, step)))
+        if workers > 1 and HostBatch._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            HostBatch._pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix='simq-stage')
+        step = (B + workers - 1) // workers
+
+        def run(fn):
+            if workers == 1:
+                fn(0, B)
+            else:
+                list(HostBatch._pool.map(lambda lo: fn(lo, min(B, lo + step)), range(0, B, step)))
+
+        run(copy_states)
         self.nonfinal.numpy()[:] = nf
         self.Bn = int(nf.sum())
         self.action.numpy()[:] = np.asarray(batch.action, dtype=np.int64)
         self.reward.numpy()[:] = np.asarray(batch.reward, dtype=np.float32)
+        if after_states is not None:
+            after_states()
+        run(copy_next)
         return self
 
     def h2d_bytes(self) -> int:
@@ -106,23 +118,32 @@ class DeviceBatch:
         """Host -> device on the current stream, except the next states: they go second over the same link on a copy
         stream, and only the s' lane of the step waits for them (``simq_set_next_state_event``), so their half of the
         transfer runs under the forward on s."""
-        cur = torch.cuda.current_stream(self.s.device)
+        self.upload_states(hb)
+        return self.upload_next(hb)
+
+    def upload_states(self, hb: HostBatch):
+        """s and the per-sample vectors, on the current stream (``hb.s`` / action / reward / nonfinal must be staged)."""
         self.s.copy_(hb.s, non_blocking=True)
         self.action.copy_(hb.action, non_blocking=True)
         self.reward.copy_(hb.reward, non_blocking=True)
         self.nonfinal.copy_(hb.nonfinal, non_blocking=True)
         self.ns_ready = None
+        self.Bn = hb.Bn
         if hb.Bn:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(self.s.device)
                 self._ev_s, self._ev_ns = torch.cuda.Event(), torch.cuda.Event()
-            self._ev_s.record(cur)               # after s (the link is shared: s first) and after every earlier reader of self.ns
+            self._ev_s.record(torch.cuda.current_stream(self.s.device))     # after s (the link is shared: s first) and after
+        return self                                                        # every earlier reader of self.ns
+
+    def upload_next(self, hb: HostBatch):
+        """The compacted next states, on the copy stream, ordered after ``upload_states``."""
+        if hb.Bn:
             self._copy_stream.wait_event(self._ev_s)
             with torch.cuda.stream(self._copy_stream):
                 self.ns[:hb.Bn].copy_(hb.ns[:hb.Bn], non_blocking=True)
                 self._ev_ns.record(self._copy_stream)
             self.ns_ready = self._ev_ns
-        self.Bn = hb.Bn
         return self
 
 
@@ -230,8 +251,8 @@ def _enqueue_train(cfg, policy_net, target_net, optimizer, batch, discount_facto
         db.nonfinal.copy_(hb.nonfinal, non_blocking=True)
         db.Bn = hb.Bn = Bn
     else:
-        hb.fill(batch)
-        db.upload(hb)
+        hb.fill(batch, after_states=lambda: db.upload_states(hb))    # s is on its way while s' is still being staged
+        db.upload_next(hb)
     train_step_device(policy, target, optimizer, db, B, discount_factor, getattr(cfg, 'grad_norm_clipping', None),
                       bool(getattr(cfg, 'use_double_dqn', True)))
     db.out2_host.copy_(db.out2, non_blocking=True)
