@@ -366,7 +366,7 @@ def run_simq(args):
 
     # ---- informational: the same step through stock PyTorch library kernels (cuDNN) on this GPU ----
     torch_gpu = None
-    if not args.no_torch_gpu and world == 1:
+    if args.torch_gpu and not args.no_torch_gpu and world == 1:
         try:
             del q_grad
             torch.cuda.empty_cache()
@@ -444,7 +444,9 @@ def main():
     ap.add_argument('--batch', type=int, default=128, help='per-GPU minibatch')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fast', action='store_true', help='skip the informational bf16-mode measurement')
-    ap.add_argument('--no-torch-gpu', action='store_true', help='skip the informational PyTorch/cuDNN-on-GPU measurement')
+    ap.add_argument('--torch-gpu', action='store_true', help='also time the step through eager PyTorch/cuDNN kernels on this GPU (informational; '
+                    'runs the oracle port on cuda tensors, so it is opt-in: profiles/r1_final_bench.json holds the numbers)')
+    ap.add_argument('--no-torch-gpu', action='store_true', help='(default; kept for older command lines)')
     ap.add_argument('--no-serial', action='store_true', help='skip the informational serial-schedule measurement')
     ap.add_argument('--no-cstar', action='store_true', help='skip the informational C=8 / A=2 measurement')
     args = ap.parse_args()
