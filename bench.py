@@ -398,7 +398,8 @@ def run_simq(args):
             'data': 'synthetic',
             'config': {'workload': workload_name(B), 'global_batch': world * B, 'parallelism': f'dp{world}',
                        'l2': 'no flush: a step streams >3 GB of activations per GPU through the 126 MB L2, evicting the 47 MB batch',
-                       'step_gflop_per_sample': STEP_GFLOP},
+                       'step_gflop_per_sample': STEP_GFLOP,
+                       'workspace_gb': float(L.simq_workspace_bytes(pol.ctx(B).handle)) / 1e9},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': hb.h2d_bytes(), 'd2h_bytes_per_step': 8,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches),

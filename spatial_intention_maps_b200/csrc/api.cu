@@ -136,7 +136,7 @@ struct simq_ctx {
     int terms;                       // 3 = parity mode (default), 1 = bf16 fast mode (simq_set_precision)
     NetDesc d;
     char* pool; size_t pool_bytes, pool_used;
-    ActSet set[2];
+    ActSet set[3];                   // 0: saved (differentiated forward), 1: scratch (no-grad forwards), 2: eval-only (concurrent target pass)
     PackedSet packed[2]; int packed_next;
     // scratch
     float* partials; float* sums; double* dpartials;
@@ -145,8 +145,8 @@ struct simq_ctx {
     Split dyA, dyB, dy2h, dy0s; float *stem_tmp, *h2_tmp;
     // second lane (see "lanes" below): its own column-sum partials and split-K / wgrad scratch, the ping-pong partner of
     // dyA, and the stash of the deferred running-statistics update of the s' pass
-    float *partials2, *wscratch2; Split dyA2; double* bn_defer;
-    cudaStream_t aux_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[4];
+    float *partials2, *wscratch2, *wscratch3; Split dyA2; double* bn_defer;
+    cudaStream_t aux_stream, aux2_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[4];
     int lanes_mode;                  // -1: read SIMQ_LANES on first use; 0 serial schedule; 1 two lanes
     cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
@@ -190,15 +190,17 @@ static void carve_all(simq_ctx* c, bool dry) {
     const size_t B = c->maxB, R25 = B * IMG25, R48 = B * 2304;
     const NetDesc& d = c->d;
     c->pool_used = 0;
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
         ActSet& S = c->set[s];
+        const bool eval_only = s == 2;             // folded-BN passes never write raw1 / raw2 and borrow another set's im2col
         S.raw0 = carve<float>(c, R48 * 64, dry);
         S.a0 = carve_split(c, R25 * 64, dry);
-        S.acol = carve_split(c, R48 * stem_kp(d.C), dry);
+        if (eval_only) { S.acol.hi = nullptr; S.acol.lo = nullptr; }
+        else S.acol = carve_split(c, R48 * stem_kp(d.C), dry);
         for (int b = 0; b < 8; ++b) {
             size_t n = R25 * d.blk[b].planes;
-            S.blk[b].raw1 = carve<float>(c, n, dry);
-            S.blk[b].raw2 = carve<float>(c, n, dry);
+            S.blk[b].raw1 = eval_only ? nullptr : carve<float>(c, n, dry);
+            S.blk[b].raw2 = eval_only ? nullptr : carve<float>(c, n, dry);
             S.blk[b].rawd = d.blk[b].has_ds ? carve<float>(c, n, dry) : nullptr;
             S.blk[b].b1 = carve_split(c, n, dry);
             S.blk[b].out = carve_split(c, n, dry);
@@ -243,6 +245,7 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->hp = carve<float>(c, (size_t)STAT_BLOCKS * 6 * 32, dry);
     c->wscratch = carve<float>(c, umma_wgrad_scratch_floats(), dry);
     c->wscratch2 = carve<float>(c, umma_wgrad_scratch_floats(), dry);
+    c->wscratch3 = carve<float>(c, umma_wgrad_scratch_floats(), dry);
     c->bn_defer = carve<double>(c, (size_t)SIMQ_N_BN * 2 * MAX_CH, dry);
     c->stem_partials = carve<float>(c, stem_wgrad_partial_floats(d.C), dry);
     c->dyA = carve_split(c, R25 * 512, dry);
@@ -311,7 +314,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
         }
     }
     c->launches0 = g_simq_launches;
-    c->aux_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1; c->next_ready = nullptr;
+    c->aux_stream = c->aux2_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1; c->next_ready = nullptr;
     for (auto& e : c->ev_pool) e = nullptr;
     for (auto& e : c->ev_done) e = nullptr;
     c->side_stream = nullptr; c->ev_in = c->ev_out = nullptr; c->graph_mode = -1; c->step_warm = false; c->pack_epoch = 0; c->graph_clock = 0; c->graph_misses = 0;
@@ -326,6 +329,7 @@ extern "C" void simq_ctx_destroy(simq_ctx* c) {
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
     for (auto e : c->ev_pool) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_done) if (e) cudaEventDestroy(e);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -375,6 +379,8 @@ struct Lane {
 };
 static Lane main_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials, c->wscratch2, nullptr}; }
 static Lane side_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials2, c->wscratch, nullptr}; }
+// eval-mode passes only: folded BatchNorm needs no column-sum partials
+static Lane eval_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, nullptr, c->wscratch3, nullptr}; }
 
 static bool lanes_enabled(simq_ctx* c) {
     if (c->lanes_mode < 0) { const char* e = getenv("SIMQ_LANES"); c->lanes_mode = e ? (atoi(e) != 0) : 1; }
@@ -383,6 +389,7 @@ static bool lanes_enabled(simq_ctx* c) {
 static int lanes_init(simq_ctx* c) {
     if (c->aux_stream) return 0;
     SIMQ_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    SIMQ_CUDA(cudaStreamCreateWithFlags(&c->aux2_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev_pool) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_done) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
@@ -482,8 +489,8 @@ static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Spli
 }
 
 static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* bn, int64_t* nbt, const float* x, int B,
-                       int x_layout, int training, ActSet& S, float* q, const Lane& L, bool reuse_acol = false) {
-    cudaStream_t s = L.s;
+                       int x_layout, int training, ActSet& S, float* q, const Lane& L, const Split* acol_src = nullptr) {
+    cudaStream_t s = L.s;      // acol_src: the stem im2col of the SAME input already expanded by another pass (skips the im2col launch)
     const NetDesc& d = c->d;
     const long long R25 = (long long)B * IMG25, R48 = (long long)B * 2304;
     const double cnt24 = (double)B * 576, cnt48 = (double)B * 2304;
@@ -492,8 +499,11 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
     if (!training) TRY(k_bn_eval_affine_all(params, bn, c->bn_table, SIMQ_N_BN, S.bnstat, s));   // running-stat BN = per-channel affine
     // stem: conv 7x7/2 -> BN -> ReLU -> maxpool 3x3/2           (resnet.py:94-97)
     if (be == SIMQ_BACKEND_UMMA) {
-        if (!reuse_acol) TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));     // else: same input as the previous pass on S
-        TRY(conv_bn(c, S, S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, L));
+        if (!acol_src) {
+            if (!S.acol.hi) { simq_set_error("run_forward: this activation set has no im2col buffer"); return 1; }
+            TRY(k_stem_im2col(x, x_layout, B, d.C, stem_kp(d.C), S.acol, s));
+        }
+        TRY(conv_bn(c, S, acol_src ? *acol_src : S.acol, R48, stem_kp(d.C), pw->stem, 64, 1, S.raw0, 0, d.stem_bn, cnt48, params, bn, nbt, -1, training, L));
     } else {
         TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
         TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, 0, L));
@@ -790,33 +800,49 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
             if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];
         if (!pw) { simq_set_error("simq_train_step: packed policy weights evicted"); return 1; }
     }
-    // The three forwards are independent: lane A (this stream) runs the s pass, lane B the two s' passes.
+    // The three forwards are independent: lane A (this stream) runs the s pass, lane B the online s' pass, lane C the target
+    // pass (tcgen05 back-end + Double DQN; otherwise lane B runs both s' passes, or the only one).
     cudaStream_t bs;
     TRY(side_stream_for(c, s, &bs));
     const Lane LA = main_lane(c, s);
     Lane LB = side_lane(c, bs);
     const bool two = bs != s && Bn > 0;
+    const bool three = two && double_dqn && c->backend == SIMQ_BACKEND_UMMA;
     if (two) TRY(lane_order(c, s, bs));                                                    // fork (after the weight packing)
     // train.py:114  online forward on s (train-mode BN, activations kept)
     TRY(run_forward(c, pw, params, bn, nbt, s_, B, x_layout, 1, c->set[0], c->q_s, LA));
     if (Bn > 0) {
-        // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again: after the
-        // s pass's update, so a concurrent s' pass stashes its batch statistics and they are applied after the join)
         if (next_ready) {
-            // the caller uploads s' on a copy stream while the s pass already runs: only the s' lane waits for it.  The event
+            // the caller uploads s' on a copy stream while the s pass already runs: only the s' lanes wait for it.  The event
             // belongs to the caller (recorded outside any capture): inside a captured step it becomes an external event-wait node
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
             SIMQ_CUDA(cudaStreamIsCapturing(LB.s, &cap));
             SIMQ_CUDA(cudaStreamWaitEvent(LB.s, next_ready, cap == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
         }
+        const Split* shared_acol = nullptr;
+        if (double_dqn && c->backend == SIMQ_BACKEND_UMMA) {
+            // both s' passes read the same stem im2col: expand it once, before lane C branches off lane B
+            TRY(k_stem_im2col(s_next, x_layout, Bn, c->d.C, stem_kp(c->d.C), c->set[1].acol, LB.s));
+            shared_acol = &c->set[1].acol;
+        }
+        Lane LC = LB;
+        ActSet* target_set = &c->set[1];
+        if (three) {
+            LC = eval_lane(c, c->aux2_stream);
+            target_set = &c->set[2];
+            TRY(lane_order(c, bs, c->aux2_stream));                                        // fork C off B: after the wait and the im2col
+        }
+        // train.py:121  online forward on s' under no_grad, still train-mode BN (updates running stats again: after the
+        // s pass's update, so a concurrent s' pass stashes its batch statistics and they are applied after the join)
         if (two) LB.defer = c->bn_defer;
-        if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, LB));
+        if (double_dqn) TRY(run_forward(c, pw, params, bn, nbt, s_next, Bn, x_layout, 1, c->set[1], c->q_no, LB, shared_acol));
         LB.defer = nullptr;
+        if (!three) LC = LB;
         // train.py:122/124  target forward, eval-mode BN
-        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, c->set[1], c->q_nt, LB,
-                        /*reuse_acol=*/double_dqn != 0));     // the online pass just expanded the same s' into set[1]
+        TRY(run_forward(c, pt, target_params, (float*)target_bn, nullptr, s_next, Bn, x_layout, 0, *target_set, c->q_nt, LC, shared_acol));
+        if (three) TRY(lane_order(c, c->aux2_stream, s));                                  // join C
         if (two) {
-            TRY(lane_order(c, bs, s));                                                     // join
+            TRY(lane_order(c, bs, s));                                                     // join B
             if (double_dqn) TRY(k_bn_running_update_all(c->bn_table, SIMQ_N_BN, c->bn_defer, bn, (long long*)nbt, s));
         }
     }
