@@ -446,7 +446,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fast', action='store_true', help='skip the informational bf16-mode measurement')
     ap.add_argument('--torch-gpu', action='store_true', help='also time the step through eager PyTorch/cuDNN kernels on this GPU (informational; '
-                    'runs the oracle port on cuda tensors, so it is opt-in: profiles/r1_final_bench.json holds the numbers)')
+                    'runs the oracle port on cuda tensors, so it is opt-in: profiles/r1_v14_bench_with_cudnn_comparator.json holds the numbers)')
     ap.add_argument('--no-torch-gpu', action='store_true', help='(default; kept for older command lines)')
     ap.add_argument('--no-serial', action='store_true', help='skip the informational serial-schedule measurement')
     ap.add_argument('--no-cstar', action='store_true', help='skip the informational C=8 / A=2 measurement')
