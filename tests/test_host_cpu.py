@@ -228,3 +228,16 @@ def test_reference_checkpoint_formats_round_trip(tmp_path):
     assert float(net.flat_momentum[po[0]]) == 1.0 and float(net.flat_momentum[po[3]]) == 4.0 and net.momentum_initialized
     p0 = net._tr_cache[0]
     assert opt.state[p0]['momentum_buffer'].data_ptr() == net.flat_momentum.data_ptr()
+
+
+def test_profile_tools_read_the_committed_launch_list():
+    """tools/launch_summary.py and tools/per_layer_table.py (the scripts behind profiles/*_summary.md and the per-layer
+    roofline tables) still parse the committed ncu launch list."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv = os.path.join(root, 'profiles', 'r1_v13_launches.csv')
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'launch_summary.py'), csv], capture_output=True, text=True, check=True).stdout
+    assert 'conv2w_umma_kernel' in out and out.startswith('Total ')
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'per_layer_table.py'), csv], capture_output=True, text=True, check=True).stdout
+    assert 'Backward (B = 128)' in out and 'of the per-layer roofline (time-weighted)' in out
