@@ -221,6 +221,10 @@ def run_simq(args):
         dist.init_process_group('nccl', device_id=dev)
 
     B = args.batch
+    if args.global_batch:                            # strong scaling: fixed global batch split over the ranks
+        if args.global_batch % world:
+            raise SystemExit(f'--global-batch {args.global_batch} is not divisible by {world} ranks')
+        B = args.global_batch // world
     torch.manual_seed(0)
     pol = networks.FCN(C_IN, A_OUT, max_batch=B).to(dev).train()
     tgt = networks.FCN(C_IN, A_OUT, max_batch=B)
@@ -229,7 +233,7 @@ def run_simq(args):
     if world > 1:                                    # identical replicas
         dist.broadcast(pol.flat_params, 0); dist.broadcast(tgt.flat_params, 0)
     opt = torch.optim.SGD(pol.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
-    batch = synth.synth_batch(B, C_IN, A_OUT, 1234 + rank, terminal_every=TERMINAL_EVERY)
+    batch = synth.synth_batch(B, C_IN, A_OUT, 1234 + rank, terminal_every=TERMINAL_EVERY, uniform=args.uniform_input)
     hb = T.HostBatch(B, C_IN).fill(batch)
     db = T.DeviceBatch(B, C_IN, dev).upload(hb)
     L = _lib.lib()
@@ -393,9 +397,9 @@ def run_simq(args):
         e2e = world * B * args.steps / (ms_e2e * 1e-3)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
-            'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None,
             'dtype': 'bf16 hi+lo split operands (3 tcgen05 MMAs per product), f32 accumulate',
-            'data': 'synthetic',
+            'data': 'synthetic (U[0,1) states)' if args.uniform_input else 'synthetic',
             'config': {'workload': workload_name(B), 'global_batch': world * B, 'parallelism': f'dp{world}',
                        'l2': 'no flush: a step streams >3 GB of activations per GPU through the 126 MB L2, evicting the 47 MB batch',
                        'step_gflop_per_sample': STEP_GFLOP,
@@ -443,6 +447,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='simq', choices=['simq', 'reference'])
     ap.add_argument('--batch', type=int, default=128, help='per-GPU minibatch')
+    ap.add_argument('--global-batch', type=int, default=0, help='strong scaling: this many samples per step over ALL ranks (e.g. 1024 = config c5); '
+                    'default 0 = weak scaling with --batch per GPU')
+    ap.add_argument('--uniform-input', action='store_true', help='U[0,1) states instead of the modelled overhead / distance / intention maps')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-fast', action='store_true', help='skip the informational bf16-mode measurement')
     ap.add_argument('--torch-gpu', action='store_true', help='also time the step through eager PyTorch/cuDNN kernels on this GPU (informational; '
