@@ -171,6 +171,19 @@ def gen_steps():
     np.savez(os.path.join(HERE, 'steps.npz'), **out)
 
 
+def gen_steps_cstar():
+    """The north_star's headline shape c* (C=8 input channels, A=2, gamma 0.85): one reference update at
+    B=16, kept in its own file so that adding it does not regenerate steps.npz."""
+    out = {}
+    key, C, rt, A, B, gamma, nsteps, seed, te = 'cstar', 8, 'lifting_robot', 2, 16, 0.85, 1, 15, 8
+    infos, grads, after, mom = run_ref_steps(C, rt, A, B, gamma, nsteps, seed, te)
+    pack_step(key, out, infos, grads, after, mom, C, A)
+    out[key + '_cfg'] = np.array([C, A, B, nsteps, seed, te], dtype=np.int64)
+    out[key + '_gamma'] = np.float64(gamma)
+    print('step', key, infos)
+    np.savez(os.path.join(HERE, 'steps_cstar.npz'), **out)
+
+
 def gen_policy():
     C, A, seed = 4, 2, 21
     cfg = make_cfg(C, 'lifting_robot', 16)
@@ -213,7 +226,7 @@ def gen_intention():
 
 
 if __name__ == '__main__':
-    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps', 'intention']
+    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps', 'steps_cstar', 'intention']
     for part in parts:
         {'manifest': gen_manifest, 'forward': gen_forward, 'policy': gen_policy, 'steps': gen_steps,
-         'intention': gen_intention}[part]()
+         'steps_cstar': gen_steps_cstar, 'intention': gen_intention}[part]()

@@ -104,12 +104,12 @@ def _check_grads(r):
     assert abs(r['grad_norm'] - gn) <= 2e-3 * gn
 
 
-@pytest.mark.parametrize('key', ['c1', 'c2', 'c3', 'traj'])
+@pytest.mark.parametrize('key', ['c1', 'c2', 'c3', 'traj', 'cstar'])
 @pytest.mark.parametrize('fused', [True, False], ids=['fused', 'autograd'])
 def test_dqn_step_matches_oracle_and_golden(key, fused):
-    """c1 / c2 / c3 (the full-size bench workload: B=128, C=5, A=1) of BASELINE.json and a 3-step trajectory; the golden losses come from the reference's own
-    train.train (tests/golden/steps.npz)."""
-    g = np.load(os.path.join(GOLD, 'steps.npz'))
+    """c1 / c2 / c3 (the full-size bench workload: B=128, C=5, A=1) of BASELINE.json, a 3-step trajectory and the north_star's headline shape
+    c* (C=8, A=2); the golden losses come from the reference's own train.train (tests/golden/steps.npz, steps_cstar.npz)."""
+    g = np.load(os.path.join(GOLD, 'steps_cstar.npz' if key == 'cstar' else 'steps.npz'))
     C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
     r = G.train_step_check(C, A, B, seed, float(g[key + '_gamma']), te, nsteps, fused=fused)
     np.testing.assert_allclose(r['loss'][0], g[key + '_loss'][0], rtol=1e-3)

@@ -68,9 +68,9 @@ def run_oracle_steps(C, A, B, nsteps, seed, te, gamma):
     return pol, mom, first, infos
 
 
-@pytest.mark.parametrize('key', ['c1', 'traj', 'c2'])
+@pytest.mark.parametrize('key', ['c1', 'traj', 'c2', 'cstar'])
 def test_dqn_step_matches_reference(key):
-    g = np.load(os.path.join(G, 'steps.npz'))
+    g = np.load(os.path.join(G, 'steps_cstar.npz' if key == 'cstar' else 'steps.npz'))
     C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
     pol, mom, first, infos = run_oracle_steps(C, A, B, nsteps, seed, te, float(g[key + '_gamma']))
     np.testing.assert_allclose([i[0] for i in infos], g[key + '_loss'], rtol=2e-4)
