@@ -241,3 +241,21 @@ def test_profile_tools_read_the_committed_launch_list():
     assert 'conv2w_umma_kernel' in out and out.startswith('Total ')
     out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'per_layer_table.py'), csv], capture_output=True, text=True, check=True).stdout
     assert 'Backward (B = 128)' in out and 'of the per-layer roofline (time-weighted)' in out
+
+
+def test_host_batch_stages_states_before_next_states():
+    """HostBatch.fill(after_states=...): when the callback runs (the caller starts the upload of s there) the states and the
+    per-sample vectors are complete and the next states have not been touched yet; afterwards everything is staged."""
+    batch = synth.synth_batch(32, 4, 2, 9, terminal_every=4)
+    hb = T.HostBatch(32, 4)
+    hb.ns.fill_(float('nan'))
+    seen = {}
+
+    def after_states():
+        seen['s_ok'] = all(np.array_equal(hb.s.numpy()[i], batch.state[i]) for i in range(32))
+        seen['vec_ok'] = hb.Bn == 24 and hb.action.tolist() == list(batch.action) and int(hb.nonfinal.sum()) == 24
+        seen['ns_untouched'] = bool(torch.isnan(hb.ns).all())
+    hb.fill(batch, after_states=after_states)
+    assert seen == {'s_ok': True, 'vec_ok': True, 'ns_untouched': True}
+    nxt = [n for n in batch.next_state if n is not None]
+    assert all(np.array_equal(hb.ns.numpy()[j], nxt[j]) for j in range(24))
