@@ -14,6 +14,7 @@ pointers.  There is no PyTorch fallback: without the CUDA library / a B200 ``for
 """
 from __future__ import annotations
 
+import copy
 import math
 from typing import List, Tuple
 
@@ -166,6 +167,31 @@ class FCN(nn.Module):
     def _bns(self):
         return [(n, m) for n, m in self.named_modules() if isinstance(m, _P) and 'running_mean' in m._buffers]
 
+    # per-object device state that a copy must NOT share: the library context (one ctypes handle = one workspace), gradient /
+    # staging buffers, and the flat vectors themselves (rebuilt by _flatten from the copied parameters)
+    _NO_COPY = ('_ctx', '_flat_grad', '_flat_grad_ext', '_batch_cache', '_intention_cache', '_ga', '_saved_x', '_tr_cache', 'flat_params',
+                'flat_bn', 'flat_nbt', 'flat_momentum', '_momentum_bound_to', '_dp_synced')
+
+    def __deepcopy__(self, memo):
+        """``copy.deepcopy(net)`` -- the common target-network idiom.  ``Parameter.__deepcopy__`` clones every tensor, which would
+        leave the copy's parameters detached from any flat vector (the library would read stale buffers) and share this
+        object's context handle; so: copy the module tree, then re-alias the copy into flat vectors and a context of its own."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in FCN._NO_COPY:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new._ctx, new._flat_grad, new._layout = None, None, self._layout
+        new.flat_momentum = self.flat_momentum.clone() if self.flat_momentum is not None else None
+        new._flatten()
+        return new
+
+    def mark_params_changed(self):
+        """Call after writing parameters through ``p.data`` / ``flat_params`` views in ways autograd's version counters do not
+        see (e.g. a Polyak target update ``target_p.data.copy_(...)``, which bumps no ``_version``): the next forward re-packs the
+        tensor-core weight shadows.  ``load_state_dict``, optimizer steps and the fused ``train.train`` need no such call."""
+        self._manual_version += 1
+
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
         self._flatten()
@@ -259,9 +285,21 @@ class FCN(nn.Module):
         return [g[po[i]:po[i + 1]].view(p.shape) for i, (_, p) in enumerate(tr)]
 
     def flat_grad(self) -> torch.Tensor:
+        """The flat fp32 gradient vector (layout of ``flat_params``).  It is the head of a slightly longer buffer whose 4-float
+        tail carries the step's (loss, td_error) report: data-parallel steps all-reduce head and tail as ONE collective."""
         if self._flat_grad is None:
-            self._flat_grad = torch.zeros_like(self.flat_params)
+            n = self.flat_params.numel()
+            self._flat_grad_ext = torch.zeros(n + 4, dtype=torch.float32, device=self.flat_params.device)
+            self._flat_grad = self._flat_grad_ext[:n]
         return self._flat_grad
+
+    def flat_grad_ext(self) -> torch.Tensor:
+        self.flat_grad()
+        if getattr(self, '_flat_grad_ext', None) is None or self._flat_grad_ext.data_ptr() != self._flat_grad.data_ptr():
+            n = self.flat_params.numel()            # _run_backward replaced the buffer (autograd aliasing): rebuild the pair
+            self._flat_grad_ext = torch.zeros(n + 4, dtype=torch.float32, device=self.flat_params.device)
+            self._flat_grad = self._flat_grad_ext[:n]
+        return self._flat_grad_ext
 
     def forward(self, x):
         tr = [p for _, p in self.trainable()]

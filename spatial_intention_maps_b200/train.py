@@ -157,18 +157,40 @@ def shard_batch(batch, rank: int, world: int):
     return Transition(*(tuple(f[lo:hi]) for f in batch))
 
 
-def allreduce_mean_(grads: torch.Tensor, out2: torch.Tensor, world: int):
-    """The path's one exchange: average the flat fp32 gradient vector (and the 2-float loss / td_error report) over
-    ranks -> gradient of the global-batch mean loss.  NCCL averages inside the collective (no extra pass over the
-    45 MB vector); back-ends without AVG (gloo, used by the CPU tests) sum and scale."""
+def allreduce_mean_(grads_ext: torch.Tensor, world: int):
+    """The path's one exchange: average the flat fp32 gradient vector over ranks -> gradient of the global-batch mean
+    loss.  ``grads_ext`` = the gradient vector followed by the step's (loss, td_error) report (``FCN.flat_grad_ext``), so the
+    report rides in the same collective.  NCCL averages inside the collective (no extra pass over the 45 MB vector);
+    back-ends without AVG (gloo, used by the CPU tests) sum and scale."""
     if dist.get_backend() == 'nccl':
-        dist.all_reduce(grads, op=dist.ReduceOp.AVG)
-        dist.all_reduce(out2, op=dist.ReduceOp.AVG)
+        dist.all_reduce(grads_ext, op=dist.ReduceOp.AVG)
         return
-    dist.all_reduce(grads)
-    grads.mul_(1.0 / world)
-    dist.all_reduce(out2)
-    out2.mul_(1.0 / world)
+    dist.all_reduce(grads_ext)
+    grads_ext.mul_(1.0 / world)
+
+
+def sync_replicas(*nets, src: int = 0):
+    """Make every rank's copy of ``nets`` identical to rank ``src``'s: parameters, BatchNorm running statistics and
+    counters, momentum.  The data-parallel step only exchanges GRADIENTS, so replicas must start identical (ranks built from
+    different RNG states, or one rank loading a checkpoint, would silently train diverged replicas); ``train`` / ``train_intention``
+    call this once per network on their first distributed step.  BatchNorm running statistics then evolve per rank (each rank
+    sees its own shard, exactly like the replicas of the reference's DataParallel, policies.py:39): call ``sync_replicas`` again
+    before checkpointing from, or syncing a target network on, anything but rank ``src`` to make rank ``src``'s statistics the
+    job's, as DataParallel does."""
+    for net in nets:
+        m = _unwrap(net)
+        for t in (m.flat_params, m.flat_bn, m.flat_nbt):
+            dist.broadcast(t, src)
+        has = torch.tensor([0 if m.flat_momentum is None else 1, 1 if m.momentum_initialized else 0], device=m.flat_params.device)
+        dist.broadcast(has, src)
+        if int(has[0]):
+            if m.flat_momentum is None or m.flat_momentum.device != m.flat_params.device:
+                m.flat_momentum = torch.zeros_like(m.flat_params)
+                m._momentum_bound_to = None
+            dist.broadcast(m.flat_momentum, src)
+            m.momentum_initialized = bool(int(has[1]))
+        m.mark_params_changed()
+        m._dp_synced = True
 
 
 def _momentum_views(net: FCN, optimizer):
@@ -208,7 +230,12 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
     clip = float(grad_norm_clipping) if grad_norm_clipping is not None else 0.0
     first = 0 if policy.momentum_initialized else 1
     lr, mom, wd = float(g['lr']), float(g.get('momentum', 0.0)), float(g.get('weight_decay', 0.0))
+    if world > 1 and not (getattr(policy, '_dp_synced', False) and getattr(target, '_dp_synced', False)):
+        sync_replicas(policy, target)
+        first = 0 if policy.momentum_initialized else 1
+    grads_ext = policy.flat_grad_ext()
     grads = policy.flat_grad()
+    out2 = db.out2 if world == 1 else grads_ext[grads.numel():grads.numel() + 2]     # DP: the report rides behind the gradients
     L = _lib.lib()
     ns_ready, db.ns_ready = getattr(db, 'ns_ready', None), None
     if ns_ready is not None:                 # s' is still on its way on the copy stream (DeviceBatch.upload)
@@ -218,11 +245,12 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
         _lib.ptr(target.flat_params), _lib.ptr(target.flat_bn), target.params_version, _lib.ptr(grads),
         _lib.ptr(policy.flat_momentum), _lib.ptr(db.s), _lib.ptr(db.ns), _lib.X_NHWC, _lib.ptr(db.action),
         _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, float(discount_factor), lr, mom, wd, clip, first,
-        1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(db.out2), _lib.stream_ptr()), 'simq_train_step')
+        1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(out2), _lib.stream_ptr()), 'simq_train_step')
     if world > 1:
-        allreduce_mean_(grads, db.out2, world)
+        allreduce_mean_(grads_ext, world)
         _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(grads), _lib.ptr(policy.flat_momentum),
                                    lr, mom, wd, clip, first, None, _lib.stream_ptr()), 'simq_sgd_step')
+        db.out2.copy_(out2, non_blocking=True)
     policy.momentum_initialized = True
     policy._manual_version += 1
 
@@ -345,14 +373,20 @@ def intention_step_device(net: FCN, optimizer, state_dev: torch.Tensor, B: int, 
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     first = 0 if net.momentum_initialized else 1
     lr, mom, wd = float(g['lr']), float(g.get('momentum', 0.0)), float(g.get('weight_decay', 0.0))
+    if world > 1 and not getattr(net, '_dp_synced', False):
+        sync_replicas(net)
+        first = 0 if net.momentum_initialized else 1
+    grads_ext = net.flat_grad_ext()
     grads = net.flat_grad()
+    rep = out1 if world == 1 else grads_ext[grads.numel():grads.numel() + 1]
     L = _lib.lib()
     _lib.check(L.simq_intention_step(ctx.handle, _lib.ptr(net.flat_params), _lib.ptr(net.flat_bn), _lib.ptr(net.flat_nbt),
                                      _lib.ptr(grads), _lib.ptr(net.flat_momentum), _lib.ptr(state_dev), B, lr, mom, wd, 0.0, first,
-                                     1 if world == 1 else 0, _lib.ptr(out1), _lib.stream_ptr()), 'simq_intention_step')
+                                     1 if world == 1 else 0, _lib.ptr(rep), _lib.stream_ptr()), 'simq_intention_step')
     if world > 1:
-        allreduce_mean_(grads, out1, world)
+        allreduce_mean_(grads_ext, world)
         _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(net.flat_params), _lib.ptr(grads), _lib.ptr(net.flat_momentum),
                                    lr, mom, wd, 0.0, first, None, _lib.stream_ptr()), 'simq_sgd_step')
+        out1.copy_(rep, non_blocking=True)
     net.momentum_initialized = True
     net._manual_version += 1

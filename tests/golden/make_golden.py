@@ -63,10 +63,10 @@ def ref_state(net):
     return {k[len('module.'):]: v.detach().clone() for k, v in net.state_dict().items()}
 
 
-def make_cfg(C, robot_type, B):
+def make_cfg(C, robot_type, B, clip=100):
     return types.SimpleNamespace(
         robot_config=[{robot_type: 1}], num_input_channels=C, checkpoint_path=None, policy_path=None,
-        final_exploration=0.01, batch_size=B, use_double_dqn=True, grad_norm_clipping=100)
+        final_exploration=0.01, batch_size=B, use_double_dqn=True, grad_norm_clipping=clip)
 
 
 def gen_manifest():
@@ -110,8 +110,8 @@ def gen_forward():
     np.savez(os.path.join(HERE, 'forward.npz'), **out)
 
 
-def run_ref_steps(C, robot_type, A, B, gamma, nsteps, seed, terminal_every):
-    cfg = make_cfg(C, robot_type, B)
+def run_ref_steps(C, robot_type, A, B, gamma, nsteps, seed, terminal_every, clip=100):
+    cfg = make_cfg(C, robot_type, B, clip)
     policy = policies.DQNPolicy(cfg, train=True)
     st = O.make_state(C, A, seed)
     load_ref(policy.policy_nets[0], st)
@@ -184,6 +184,34 @@ def gen_steps_cstar():
     np.savez(os.path.join(HERE, 'steps_cstar.npz'), **out)
 
 
+def gen_steps_clip():
+    """train.py:133-134 with the clip ENGAGED (max-norm 1 and 5: the gradient norm of these batches is ~10-40, so
+    coef < 1) and with ``grad_norm_clipping: None`` (the branch that skips clip_grad_norm_); ``_grad_digest`` holds the
+    gradients AFTER the in-place rescale, ``_grad_norm`` their norm (= the max-norm when the clip is active)."""
+    out = {}
+    for key, clip in (('clip1', 1.0), ('clip5', 5.0), ('clipnone', None)):
+        C, rt, A, B, gamma, nsteps, seed, te = 4, 'lifting_robot', 2, 16, 0.75, 2, 16, 8
+        infos, grads, after, mom = run_ref_steps(C, rt, A, B, gamma, nsteps, seed, te, clip)
+        pack_step(key, out, infos, grads, after, mom, C, A)
+        out[key + '_cfg'] = np.array([C, A, B, nsteps, seed, te], dtype=np.int64)
+        out[key + '_gamma'] = np.float64(gamma)
+        out[key + '_clip'] = np.float64(-1.0 if clip is None else clip)
+        print('step', key, infos, float(out[key + '_grad_norm']))
+    np.savez(os.path.join(HERE, 'steps_clip.npz'), **out)
+
+
+def gen_steps_cstar128():
+    """c* at the north_star's full batch: C=8, A=2, gamma 0.85, B=128, every 64th transition terminal (digests only)."""
+    out = {}
+    key, C, rt, A, B, gamma, nsteps, seed, te = 'cstar128', 8, 'lifting_robot', 2, 128, 0.85, 1, 17, 64
+    infos, grads, after, mom = run_ref_steps(C, rt, A, B, gamma, nsteps, seed, te)
+    pack_step(key, out, infos, grads, after, mom, C, A)
+    out[key + '_cfg'] = np.array([C, A, B, nsteps, seed, te], dtype=np.int64)
+    out[key + '_gamma'] = np.float64(gamma)
+    print('step', key, infos)
+    np.savez(os.path.join(HERE, 'steps_cstar128.npz'), **out)
+
+
 def gen_policy():
     C, A, seed = 4, 2, 21
     cfg = make_cfg(C, 'lifting_robot', 16)
@@ -226,7 +254,8 @@ def gen_intention():
 
 
 if __name__ == '__main__':
-    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps', 'steps_cstar', 'intention']
+    parts = sys.argv[1:] or ['manifest', 'forward', 'policy', 'steps', 'steps_cstar', 'intention', 'steps_clip', 'steps_cstar128']
     for part in parts:
         {'manifest': gen_manifest, 'forward': gen_forward, 'policy': gen_policy, 'steps': gen_steps,
-         'steps_cstar': gen_steps_cstar, 'intention': gen_intention}[part]()
+         'steps_cstar': gen_steps_cstar, 'intention': gen_intention, 'steps_clip': gen_steps_clip,
+         'steps_cstar128': gen_steps_cstar128}[part]()

@@ -160,7 +160,7 @@ class Cfg:
 
 
 def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_lib.BACKEND_UMMA, fused=True, with_fp64=False, resync=True,
-                     double_dqn=True):
+                     double_dqn=True, grad_clip=100.0, setup=None):
     """nsteps updates on the GPU (fused simq_train_step, or the autograd path with a stock SGD exactly as
     the reference's train.py drives it) and in the oracle.  Returns a dict of error metrics."""
     pol, st = make_net(Cin, A, seed, max_batch=B, backend=backend)
@@ -171,6 +171,9 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
     opt = torch.optim.SGD(pol.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)       # train.py:186
     cfg = Cfg(B, Cin)
     cfg.use_double_dqn = double_dqn
+    cfg.grad_norm_clipping = grad_clip                    # train.py:133: None skips clip_grad_norm_
+    if setup is not None:
+        setup(pol)
     o_pol, o_tgt, o_mom = O.clone_state(st), O.clone_state(st), None
     out = {'loss': [], 'td': [], 'loss_ref': [], 'td_ref': []}
     names = O.trainable_names(Cin, A)
@@ -180,7 +183,7 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
             s_, a_, r_, ns_, m_ = batch_tensors(batch)
             r64 = O.dqn_step(O.clone_state(st, torch.float64), O.clone_state(st, torch.float64), None, s_.double(), a_,
                              r_.double(), ns_.double(), m_, discount=gamma, apply_update=False)
-        r = O.dqn_step(o_pol, o_tgt, o_mom, *batch_tensors(batch), discount=gamma, double_dqn=double_dqn)
+        r = O.dqn_step(o_pol, o_tgt, o_mom, *batch_tensors(batch), discount=gamma, double_dqn=double_dqn, grad_clip=grad_clip)
         o_mom = r['momentum']
         if fused:
             info = simq_train.train(cfg, pol, tgt, opt, batch, None, gamma)
@@ -204,7 +207,14 @@ def train_step_check(Cin, A, B, seed, gamma, terminal_every, nsteps=1, backend=_
         if step == 0:
             out['grad_rel_l2'] = {n: rel_l2(gmap[n], r['grads'][n]) for n in names}
             gn = float(torch.sqrt(sum((gmap[n].double() ** 2).sum() for n in names)))
-            out['grad_norm'], out['grad_norm_ref'] = gn, r['grad_norm'] * min(1.0, 100.0 / (r['grad_norm'] + 1e-6))
+            coef = 1.0 if grad_clip is None else min(1.0, float(grad_clip) / (r['grad_norm'] + 1e-6))
+            out['grad_norm'], out['grad_norm_ref'], out['clip_coef_ref'] = gn, r['grad_norm'] * coef, coef
+            # the UPDATE itself (clip coefficient x momentum rule x lr): p_after - p_before, ours vs the oracle's
+            sd0 = pol.state_dict()
+            d_mine = torch.cat([(sd0[n].detach().double().cpu() - st[n].double()).reshape(-1) for n in names])
+            d_ref = torch.cat([(o_pol[n].double() - st[n].double()).reshape(-1) for n in names])
+            out['update_rel_l2'] = float((d_mine - d_ref).norm() / d_ref.norm().clamp_min(1e-30))
+            out['update_norm_ratio'] = float(d_mine.norm() / d_ref.norm().clamp_min(1e-30))
             flat = lambda d: torch.cat([d[n].detach().double().cpu().reshape(-1) for n in names])
             out['flat_grad_rel_l2'] = rel_l2(flat(gmap), flat(r['grads']))
             out['grad_abs'] = {n: float((gmap[n].double().cpu() - r['grads'][n].double()).abs().max()) for n in names}
@@ -248,7 +258,8 @@ def reference_style_train(cfg, policy_net, target_net, optimizer, batch, discoun
     loss = F.smooth_l1_loss(q, y)
     optimizer.zero_grad()
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(policy_net.parameters(), cfg.grad_norm_clipping)
+    if cfg.grad_norm_clipping is not None:                                     # train.py:133
+        torch.nn.utils.clip_grad_norm_(policy_net.parameters(), cfg.grad_norm_clipping)
     optimizer.step()
     return {'td_error': td.mean().item(), 'loss': loss.item()}
 

@@ -104,16 +104,33 @@ def _check_grads(r):
     assert abs(r['grad_norm'] - gn) <= 2e-3 * gn
 
 
-@pytest.mark.parametrize('key', ['c1', 'c2', 'c3', 'traj', 'cstar'])
+GOLDEN_FILE = {'cstar': 'steps_cstar.npz', 'cstar128': 'steps_cstar128.npz', 'clip1': 'steps_clip.npz', 'clip5': 'steps_clip.npz',
+               'clipnone': 'steps_clip.npz'}
+
+
+@pytest.mark.parametrize('key', ['c1', 'c2', 'c3', 'traj', 'cstar', 'cstar128', 'clip1', 'clip5', 'clipnone'])
 @pytest.mark.parametrize('fused', [True, False], ids=['fused', 'autograd'])
 def test_dqn_step_matches_oracle_and_golden(key, fused):
-    """c1 / c2 / c3 (the full-size bench workload: B=128, C=5, A=1) of BASELINE.json, a 3-step trajectory and the north_star's headline shape
-    c* (C=8, A=2); the golden losses come from the reference's own train.train (tests/golden/steps.npz, steps_cstar.npz)."""
-    g = np.load(os.path.join(GOLD, 'steps_cstar.npz' if key == 'cstar' else 'steps.npz'))
+    """c1 / c2 / c3 (the full-size bench workload: B=128, C=5, A=1) of BASELINE.json, a 3-step trajectory, the north_star's headline shape
+    c* (C=8, A=2) at B=16 and at its full batch 128, and the three branches of train.py:133-134: clip_grad_norm_ engaged (max-norm 1 and 5
+    against a gradient norm of ~21: coef < 1), inactive (max-norm 100, every other case) and skipped (``grad_norm_clipping: None``).
+    The golden losses / gradient norms come from the reference's own train.train (tests/golden/steps*.npz)."""
+    g = np.load(os.path.join(GOLD, GOLDEN_FILE.get(key, 'steps.npz')))
     C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
-    r = G.train_step_check(C, A, B, seed, float(g[key + '_gamma']), te, nsteps, fused=fused)
+    clip = 100.0
+    if key + '_clip' in g:
+        clip = None if float(g[key + '_clip']) < 0 else float(g[key + '_clip'])
+    r = G.train_step_check(C, A, B, seed, float(g[key + '_gamma']), te, nsteps, fused=fused, grad_clip=clip)
     np.testing.assert_allclose(r['loss'][0], g[key + '_loss'][0], rtol=1e-3)
     np.testing.assert_allclose(r['td'][0], g[key + '_td'][0], rtol=1e-3)
+    if key.startswith('clip'):
+        # the gradients left in .grad are the rescaled ones: their norm equals the reference's (= max-norm when engaged)
+        np.testing.assert_allclose(r['grad_norm'], float(g[key + '_grad_norm']), rtol=2e-3)
+        assert (r['clip_coef_ref'] < 0.5) == (clip is not None), r['clip_coef_ref']
+        # and the parameter UPDATE (coef x lr x momentum rule) matches in size and direction
+        assert abs(r['update_norm_ratio'] - 1.0) < 5e-3 and r['update_rel_l2'] < 3e-2, (r['update_norm_ratio'], r['update_rel_l2'])
+        # step 2 starts from the oracle's state after ITS clipped update: equals the reference's second loss
+        np.testing.assert_allclose(r['loss_ref'], g[key + '_loss'], rtol=2e-4)
     # multi-step: every step restarts from the oracle's state (teacher forcing, see gpu_checks.train_step_check):
     # free-running B=8 trajectories diverge chaotically (a Double-DQN arg-max flip moves the loss by several %;
     # make_golden.py notes 1e-5 -> 30 % by step 5 even for the fp32 oracle against the reference)

@@ -259,3 +259,37 @@ def test_host_batch_stages_states_before_next_states():
     assert seen == {'s_ok': True, 'vec_ok': True, 'ns_untouched': True}
     nxt = [n for n in batch.next_state if n is not None]
     assert all(np.array_equal(hb.ns.numpy()[j], nxt[j]) for j in range(24))
+
+
+def test_deepcopy_gives_an_independent_network_with_its_own_flat_storage():
+    """``copy.deepcopy(policy_net)`` is the common target-network idiom: the copy's parameters and buffers must be views into
+    ITS OWN flat vectors (the library reads those), not clones detached from them, and it must not share the context."""
+    import copy
+    net = networks.FCN(4, 2)
+    net.flat_momentum = torch.ones_like(net.flat_params)
+    cp = copy.deepcopy(net)
+    lo, hi = cp.flat_params.data_ptr(), cp.flat_params.data_ptr() + 4 * cp.flat_params.numel()
+    for _, p in cp.trainable():
+        assert lo <= p.data_ptr() < hi
+    assert lo <= cp.conv3.weight.data_ptr() < hi and cp.flat_params.data_ptr() != net.flat_params.data_ptr()
+    b0 = cp.flat_bn.data_ptr()
+    assert b0 <= cp.bn1.running_mean.data_ptr() < b0 + 4 * cp.flat_bn.numel()
+    assert cp._ctx is None and cp.flat_momentum.data_ptr() != net.flat_momentum.data_ptr()
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), cp.state_dict().values()))
+    with torch.no_grad():
+        cp.conv3.weight.add_(1.0)                      # writes through the parameter land in the copy's flat vector only
+    off = cp._layout[2][-3]
+    assert abs(float((cp.flat_params[off:off + 64] - net.flat_params[off:off + 64]).min()) - 1.0) < 1e-6
+    sd = net.state_dict()
+    cp.load_state_dict(sd)
+    assert torch.equal(cp.flat_params, net.flat_params)
+
+
+def test_mark_params_changed_bumps_the_version_data_writes_do_not():
+    net = networks.FCN(4, 2)
+    v0 = net.params_version
+    for p in net.parameters():
+        p.data.mul_(0.5)                               # invisible to autograd's version counters (Polyak-style update)
+    assert net.params_version == v0
+    net.mark_params_changed()
+    assert net.params_version > v0

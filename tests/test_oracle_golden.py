@@ -53,14 +53,14 @@ def _batch_tensors(batch):
     return s, torch.tensor(batch.action), torch.tensor(batch.reward, dtype=torch.float32), ns, mask
 
 
-def run_oracle_steps(C, A, B, nsteps, seed, te, gamma):
+def run_oracle_steps(C, A, B, nsteps, seed, te, gamma, clip=100.0):
     pol = O.make_state(C, A, seed)
     tgt = O.clone_state(pol)
     mom, first = None, None
     infos = []
     for step in range(nsteps):
         batch = synth.synth_batch(B, C, A, seed + 1000 * step, terminal_every=te)
-        r = O.dqn_step(pol, tgt, mom, *_batch_tensors(batch), discount=gamma)
+        r = O.dqn_step(pol, tgt, mom, *_batch_tensors(batch), discount=gamma, grad_clip=clip)
         mom = r['momentum']
         infos.append((r['loss'], r['td_error']))
         if first is None:
@@ -68,11 +68,24 @@ def run_oracle_steps(C, A, B, nsteps, seed, te, gamma):
     return pol, mom, first, infos
 
 
-@pytest.mark.parametrize('key', ['c1', 'traj', 'c2', 'cstar'])
+GOLDEN_FILE = {'cstar': 'steps_cstar.npz', 'cstar128': 'steps_cstar128.npz', 'clip1': 'steps_clip.npz', 'clip5': 'steps_clip.npz',
+               'clipnone': 'steps_clip.npz'}
+
+
+@pytest.mark.parametrize('key', ['c1', 'traj', 'c2', 'cstar', 'clip1', 'clip5', 'clipnone', 'cstar128'])
 def test_dqn_step_matches_reference(key):
-    g = np.load(os.path.join(G, 'steps_cstar.npz' if key == 'cstar' else 'steps.npz'))
+    """clip1 / clip5: clip_grad_norm_ ENGAGED (train.py:133-134, coef < 1); clipnone: ``grad_norm_clipping: None`` (the branch
+    that skips it); cstar128: the north_star's headline shape at its full batch (C=8, A=2, B=128)."""
+    g = np.load(os.path.join(G, GOLDEN_FILE.get(key, 'steps.npz')))
     C, A, B, nsteps, seed, te = [int(v) for v in g[key + '_cfg']]
-    pol, mom, first, infos = run_oracle_steps(C, A, B, nsteps, seed, te, float(g[key + '_gamma']))
+    clip = 100.0
+    if key + '_clip' in g:
+        clip = None if float(g[key + '_clip']) < 0 else float(g[key + '_clip'])
+    pol, mom, first, infos = run_oracle_steps(C, A, B, nsteps, seed, te, float(g[key + '_gamma']), clip)
+    if clip is not None:                       # the golden gradients are the ones clip_grad_norm_ rescaled in place
+        first = dict(first, grad_norm=min(first['grad_norm'], clip * first['grad_norm'] / (first['grad_norm'] + 1e-6)))
+        if clip < 100.0:
+            assert first['grad_norm'] < 1.0001 * clip and float(g[key + '_grad_norm']) > 0.999 * clip   # the clip really is active
     np.testing.assert_allclose([i[0] for i in infos], g[key + '_loss'], rtol=2e-4)
     np.testing.assert_allclose([i[1] for i in infos], g[key + '_td'], rtol=2e-4)
     names = O.trainable_names(C, A)
