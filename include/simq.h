@@ -9,7 +9,8 @@
  * Conventions: every function returns 0 on success, nonzero on error (message: simq_last_error(),
  * thread-local).  No exceptions, no ownership transfer: all tensors are caller-owned DEVICE
  * pointers that must stay valid until `stream` has executed the call's work.  The library owns
- * only the ctx workspace.  A ctx is bound to one device and is not thread-safe.
+ * only the ctx workspace.  A ctx is bound to one device and is not thread-safe; DISTINCT contexts may be used from
+ * different threads concurrently (scratch, launch counters and error words are per context, profiling state per thread).
  *
  * Flat parameter vector ("params"/"grads"/"momentum"): the 70 trainable tensors of networks.FCN in
  * reference state_dict order (networks.py:7-14, resnet.py:52-68; resnet18.fc.* excluded — it never
@@ -88,6 +89,11 @@ int simq_fcn_backward(simq_ctx*, const float* params, const float* x, int x_layo
 int simq_dqn_tail(simq_ctx*, const float* q_s, const float* q_next_online, const float* q_next_target,
                   const int64_t* action, const float* reward, const uint8_t* nonfinal, float gamma,
                   int B, int Bn, int double_dqn, float* out2, float* dq, simq_stream stream);
+
+/* Input errors that only the device can see (an action index outside [0, A*96*96): the reference's gather raises, train.py:115)
+ * never index out of bounds: the kernel sets a bit in the context's device error word and the step reports NaN loss / td_error.
+ * This call synchronises `stream`, returns nonzero (message: simq_last_error) if a bit is set, and clears the word. */
+int simq_check_device_errors(simq_ctx*, simq_stream stream);
 
 /* Replaces clip_grad_norm_ + SGD.step (train.py:133-135, ctor :186) over the flat vectors.
  * first_step!=0: momentum := g (torch.optim.SGD first-step rule).  clip_norm<=0: no clipping.

@@ -1,0 +1,38 @@
+"""Stage the UNMODIFIED reference implementation of the hot path for the CPU arm of bench.py.  TEST / MEASUREMENT
+INFRASTRUCTURE ONLY (never imported by the product package).
+
+The reference is Python: its "build" is byte-compilation.  This recipe compiles the four modules of the path -- where they lie
+under /root/reference -- to sourceless ``oracle/_ref/<module>.pyc`` files (outputs only; no reference source enters the
+repository; ``oracle/_ref/`` is git-ignored but NOT gpurun-ignored, so it travels to the GPU box like our own built ``.so``).
+``oracle/ref_runner.py`` imports them with ``envs`` / ``utils`` stubbed (pybullet & co. are not installed)
+and drives ``train.train`` unmodified.  Run by ``__graft_entry__.build()`` when /root/reference is present.
+
+    python oracle/build_ref.py
+"""
+import os
+import py_compile
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get('SIMQ_REFERENCE_DIR', '/root/reference')
+MODULES = ('networks', 'resnet', 'policies', 'train')       # networks.py:6-26, resnet.py:19-120, policies.py:11-146, train.py:108-158
+
+
+def build(verbose=True) -> bool:
+    if not os.path.isdir(REF):
+        if verbose:
+            print(f'{REF} not present: keeping whatever oracle/_ref already holds')
+        return False
+    out = os.path.join(HERE, '_ref')
+    os.makedirs(out, exist_ok=True)
+    for m in MODULES:
+        py_compile.compile(os.path.join(REF, m + '.py'), cfile=os.path.join(out, m + '.pyc'), doraise=True, optimize=0)
+    with open(os.path.join(out, 'BUILD_INFO'), 'w') as f:
+        f.write(f'python {sys.version.split()[0]}; byte-compiled from {REF}: ' + ', '.join(m + '.py' for m in MODULES) + '\n')
+    if verbose:
+        print('staged', ', '.join(m + '.pyc' for m in MODULES), 'into', out)
+    return True
+
+
+if __name__ == '__main__':
+    build()

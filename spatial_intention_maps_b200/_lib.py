@@ -40,6 +40,7 @@ _PROTOS = {
     'simq_fcn_forward': (C.c_int, [_c_ctx, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_uint64, _p]),
     'simq_fcn_backward': (C.c_int, [_c_ctx, _p, _p, C.c_int, _p, C.c_int, _p, _p]),
     'simq_dqn_tail': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, _p, C.c_float, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
+    'simq_check_device_errors': (C.c_int, [_c_ctx, _p]),
     'simq_sgd_step': (C.c_int, [_c_ctx, _p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _p, _p]),
     'simq_train_step': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, C.c_uint64, _p, _p, _p, _p, C.c_int, _p, _p, _p,
                                   C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

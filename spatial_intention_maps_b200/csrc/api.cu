@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-long long g_simq_launches = 0;
+thread_local long long g_simq_launches = 0;
 static thread_local char g_err[512] = "";
 
 void simq_set_error(const char* fmt, ...) {
@@ -26,9 +26,10 @@ extern "C" int simq_version(void) { return 1; }
 // per-kernel-class timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
-static std::vector<cudaEvent_t> g_prof_pool;
+// (thread-local: simq_profile has no context argument; a profile belongs to the thread that enabled it)
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
 void prof_enable(bool on) { g_prof_on = on; }
 void prof_mark(int cls, bool begin, double flops, cudaStream_t s) {
     if (!g_prof_on) return;
@@ -150,7 +151,8 @@ struct simq_ctx {
     int lanes_mode;                  // -1: read SIMQ_LANES on first use; 0 serial schedule; 1 two lanes
     cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
-    long long launches0;
+    int* dev_err;                    // device error word (SIMQ_DEVERR_*), read by simq_check_device_errors
+    long long launch_total;          // kernels launched through this context (entry points credit their launches: LaunchScope)
     // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; long long launches; uint64_t last_use; };
     std::vector<GraphEntry> graphs;
@@ -160,6 +162,13 @@ struct simq_ctx {
     uint64_t pack_epoch, graph_clock; // pack_epoch: bumped whenever a packed-weight slot changes owner
     int graph_misses;                // consecutive captures without a replay: a caller whose arguments change every call
                                      // (e.g. a per-step learning-rate schedule) is better served by eager launches
+};
+
+// credits the launches of one entry point (counted per thread by SIMQ_LAUNCH_CHECK) to the context it was called on
+struct LaunchScope {
+    simq_ctx* c; long long l0;
+    explicit LaunchScope(simq_ctx* ctx) : c(ctx), l0(g_simq_launches) {}
+    ~LaunchScope() { if (c) c->launch_total += g_simq_launches - l0; }
 };
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -261,6 +270,7 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->dq = carve<float>(c, B * 2 * 9216, dry);
     c->per_sample = carve<float>(c, B * 2, dry);
     c->best = carve<long long>(c, B, dry);
+    c->dev_err = carve<int>(c, 64, dry);
 }
 
 extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch) {
@@ -313,7 +323,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
             if (e != cudaSuccess) { simq_set_error("simq_ctx_create: table upload -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
         }
     }
-    c->launches0 = g_simq_launches;
+    c->launch_total = 0;
     c->aux_stream = c->aux2_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1; c->next_ready = nullptr;
     for (auto& e : c->ev_pool) e = nullptr;
     for (auto& e : c->ev_done) e = nullptr;
@@ -350,7 +360,7 @@ extern "C" int simq_set_precision(simq_ctx* c, int mode) {
     return 0;
 }
 extern "C" size_t simq_workspace_bytes(const simq_ctx* c) { return c ? c->pool_bytes : 0; }
-extern "C" int64_t simq_launch_count(const simq_ctx* c) { return c ? (int64_t)(g_simq_launches - c->launches0) : 0; }
+extern "C" int64_t simq_launch_count(const simq_ctx* c) { return c ? (int64_t)c->launch_total : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -424,7 +434,7 @@ static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Sp
         UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
         ep.terms = c->terms;
         // the lane's scratch is idle whenever one of its forward convs / dgrads runs: lend it to the split-K path of small problems
-        umma_set_splitk_scratch(out == L.scratch ? nullptr : L.scratch, umma_wgrad_scratch_floats());
+        if (out != L.scratch) { ep.splitk_scratch = L.scratch; ep.splitk_floats = umma_wgrad_scratch_floats(); }
         return k_conv_umma(a, w, N, ntaps, out, ep, L.s);
     }
     return k_conv_fma(A, rows, K, W, N, ntaps, out, ep, L.s);
@@ -575,6 +585,7 @@ static int check_fwd_args(simq_ctx* c, const void* params, const void* bn, const
 extern "C" int simq_fcn_forward(simq_ctx* c, const float* params, float* bn, int64_t* nbt, const float* x, int B, int x_layout,
                                 int training, int save_for_backward, float* q, uint64_t params_version, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, x, B));
+    LaunchScope launch_scope(c);
     if (!q) { simq_set_error("simq_fcn_forward: q is NULL"); return 1; }
     cudaStream_t s = (cudaStream_t)stream;
     int err;
@@ -755,6 +766,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
 extern "C" int simq_fcn_backward(simq_ctx* c, const float* params, const float* x, int x_layout, const float* dq, int B,
                                  float* grads, simq_stream stream) {
     if (!c || !params || !x || !dq || !grads) { simq_set_error("simq_fcn_backward: NULL argument"); return 1; }
+    LaunchScope launch_scope(c);
     cudaStream_t s = (cudaStream_t)stream;
     PackedSet* pw = nullptr;
     for (int i = 0; i < 2; ++i)
@@ -770,15 +782,29 @@ extern "C" int simq_dqn_tail(simq_ctx* c, const float* q_s, const float* q_next_
                              const int64_t* action, const float* reward, const uint8_t* nonfinal, float gamma, int B, int Bn,
                              int double_dqn, float* out2, float* dq, simq_stream stream) {
     if (!c || !q_s || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_dqn_tail: NULL argument"); return 1; }
+    LaunchScope launch_scope(c);
     if (B < 1 || B > c->maxB || Bn < 0 || Bn > B) { simq_set_error("simq_dqn_tail: B=%d Bn=%d", B, Bn); return 1; }
     if (Bn > 0 && (!q_next_target || (double_dqn && !q_next_online))) { simq_set_error("simq_dqn_tail: next-state Q-maps missing"); return 1; }
     return k_dqn_tail(q_s, q_next_online, q_next_target, (const long long*)action, reward, nonfinal, gamma, B, Bn, c->d.A, double_dqn,
-                      c->per_sample, c->best, out2, dq, (cudaStream_t)stream);
+                      c->per_sample, c->best, out2, dq, c->dev_err, (cudaStream_t)stream);
+}
+
+extern "C" int simq_check_device_errors(simq_ctx* c, simq_stream stream) {
+    if (!c) { simq_set_error("simq_check_device_errors: ctx is NULL"); return 1; }
+    int flags = 0;
+    SIMQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    SIMQ_CUDA(cudaMemcpy(&flags, c->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!flags) return 0;
+    SIMQ_CUDA(cudaMemset(c->dev_err, 0, sizeof(int)));
+    if (flags & SIMQ_DEVERR_ACTION_RANGE) simq_set_error("action index outside [0, %d) in the replay batch (train.py:115 would raise in gather)", c->d.A * 9216);
+    else simq_set_error("device error flags 0x%x", flags);
+    return 1;
 }
 
 extern "C" int simq_sgd_step(simq_ctx* c, float* params, float* grads, float* momentum, float lr, float mom, float wd,
                              float clip_norm, int first_step, float* grad_norm_out, simq_stream stream) {
     if (!c || !params || !grads || !momentum) { simq_set_error("simq_sgd_step: NULL argument"); return 1; }
+    LaunchScope launch_scope(c);
     return k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, grad_norm_out,
                       (cudaStream_t)stream);
 }
@@ -849,7 +875,7 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
     // train.py:115-129; dL/dQ is one-hot per sample
     float* dq = c->dq;
     TRY(k_dqn_tail(c->q_s, c->q_no, c->q_nt, (const long long*)action, reward, nonfinal, gamma, B, Bn, c->d.A, double_dqn,
-                   c->per_sample, c->best, out2, dq, s));
+                   c->per_sample, c->best, out2, dq, c->dev_err, s));
     // train.py:131-135
     TRY(run_backward(c, pw, params, s_, x_layout, dq, B, grads, s));
     if (apply_update)
@@ -954,6 +980,7 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
                                const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
                                int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, s_, B));
+    LaunchScope launch_scope(c);
     if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
     if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
     // whether the packed target weights are reused decides whether their pack kernels are part of the graph
@@ -991,6 +1018,7 @@ extern "C" int simq_gather_rows(const float* src, const int64_t* idx, int n, int
 extern "C" int simq_bce_tail(simq_ctx* c, const float* q, const float* target, int64_t target_stride, int64_t n, float* out1, float* dq,
                              simq_stream stream) {
     if (!c || !q || !target || !out1 || !dq || n < 1 || target_stride < 1) { simq_set_error("simq_bce_tail: bad argument"); return 1; }
+    LaunchScope launch_scope(c);
     return k_bce_tail(q, target, target_stride, n, out1, dq, c->dpartials, (cudaStream_t)stream);
 }
 
@@ -998,6 +1026,7 @@ extern "C" int simq_intention_step(simq_ctx* c, float* params, float* bn, int64_
                                    const float* state, int B, float lr, float mom, float wd, float clip_norm, int first_step,
                                    int apply_update, float* out1, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, state, B));
+    LaunchScope launch_scope(c);
     if (!grads || !momentum || !out1) { simq_set_error("simq_intention_step: NULL argument"); return 1; }
     if (c->d.A != 1) { simq_set_error("simq_intention_step: the intention net has one output channel (A=%d)", c->d.A); return 1; }
     std::vector<uint64_t> key = {2, (uint64_t)params, (uint64_t)bn, (uint64_t)nbt, (uint64_t)grads, (uint64_t)momentum, (uint64_t)state,
@@ -1022,6 +1051,7 @@ extern "C" int simq_intention_step(simq_ctx* c, float* params, float* bn, int64_
 extern "C" int simq_greedy_action(simq_ctx* c, const float* params, const float* bn, const float* x, int B, int x_layout,
                                   int64_t* action_out, float* q, uint64_t params_version, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, x, B));
+    LaunchScope launch_scope(c);
     if (!action_out) { simq_set_error("simq_greedy_action: action_out is NULL"); return 1; }
     // the env loop calls this once per step with the same buffers: replay one graph (policies.py:47-74)
     const bool hit = packed_hit(c, params, params_version);
@@ -1058,6 +1088,7 @@ extern "C" const char* simq_debug_tensor_name(int id) {
 
 extern "C" int simq_debug_get(simq_ctx* c, int set, int id, int B, float* out, int64_t* chw, simq_stream stream) {
     if (!c || set < 0 || set > 1 || !out) { simq_set_error("simq_debug_get: bad argument"); return 1; }
+    LaunchScope launch_scope(c);
     ActSet& S = c->set[set];
     cudaStream_t s = (cudaStream_t)stream;
     Split none{nullptr, nullptr};
@@ -1083,6 +1114,7 @@ extern "C" int simq_debug_get(simq_ctx* c, int set, int id, int B, float* out, i
 extern "C" int simq_test_conv(simq_ctx* c, int backend, int mode, int B, int Cin, int Cout, int k, const float* a, const float* a2,
                               const float* w, float* out, simq_stream stream) {
     if (!c || !a || !out || (mode != 2 && !w) || (mode == 2 && !a2)) { simq_set_error("simq_test_conv: NULL argument"); return 1; }
+    LaunchScope launch_scope(c);
     if (B < 1 || B > c->maxB || Cin > 512 || Cout > 512 || Cin % 16 || Cout % 16 || (k != 1 && k != 3)) { simq_set_error("simq_test_conv: bad shape"); return 1; }
     cudaStream_t s = (cudaStream_t)stream;
     const long long R25 = (long long)B * IMG25;

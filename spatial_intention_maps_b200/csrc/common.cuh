@@ -74,7 +74,8 @@ __host__ __device__ inline void bilin_src(int dst, int in_size, int out_size, in
     w0 = 1.0f - w1;
 }
 
-extern long long g_simq_launches;     // kernels launched by this library (host counter)
+extern thread_local long long g_simq_launches;     // kernels launched by this library on the calling thread (host counter;
+                                                   // api.cu credits the difference over an entry point to that call's context)
 void simq_set_error(const char* fmt, ...);
 
 #define SIMQ_CUDA(expr)                                                                          \

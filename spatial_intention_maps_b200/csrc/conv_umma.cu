@@ -1029,154 +1029,6 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
     }
 }
 
-// Windowed CTA-pair wgrad for the 3x3 convs (experimental, SIMQ_WGRAD_WINDOW=1): the three taps of one kernel row
-// (dx = -1, 0, +1) contract the SAME dY rows against X rows that differ by one position, so a CTA keeps three accumulators
-// (256 co x 128 ci each, 3 x 128 TMEM columns) and stages, per 64-row K step, its 128 dY channels once and ONE 72-row X
-// window (rows p0 + dy*25 - 1 ...); tap dx reads the window through an MN-major descriptor advanced by (1 + dx) rows of 128
-// bytes (SWIZZLE_128B follows the absolute shared-memory address, as in conv2w_umma_kernel).  50 KB per stage feed
-// 3 x (256 x 128 x 64) MMA blocks instead of 64 KB per 256 x 256 x 64: -48 % L2 -> SM bytes per MMA.
-// grid = (2 * Cout/256, Cin/128, 3 * nsplit); partial layout as wgrad2_umma_kernel.
-template <int TERMS>
-struct Wgrad3Cfg {
-    static constexpr int XWIN_ROWS = 72;                      // 64 + 2, rounded up to the 8-row swizzle atom
-    static constexpr int A_BYTES = 128 * UM_BK * 2;           // dY plane: 2 blocks of [64 rows][64 co]
-    static constexpr int B_BYTES = XWIN_ROWS * 64 * 2;        // X plane: one block of [72 rows][64 ci] (this CTA's half of 128 ci)
-    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
-    static constexpr int B_OFF = PLANES * A_BYTES;
-    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-};
-
-template <int TERMS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
-wgrad3_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
-                   const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo, long long rows, int Cout,
-                   int Cin, int nsplit, long long chunk, float* __restrict__ partial) {
-    using Cfg = Wgrad3Cfg<TERMS>;
-    static_assert(Cfg::STAGE_BYTES % 1024 == 0 && Cfg::B_BYTES % 1024 == 0, "stage planes must keep the 1024-byte swizzle alignment");
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * Cfg::STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int co0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;      // this CTA's dY channels (= its accumulator rows)
-    const int ci_pair0 = blockIdx.y * 128;                          // the pair's X channels
-    const int ci0 = ci_pair0 + (int)rank * 64;                      // the half this CTA stages
-    const int dyg = blockIdx.z % 3, sp = blockIdx.z / 3;            // kernel row dy = dyg - 1, row split
-    const int xoff = (dyg - 1) * PITCH - 1;                         // window row 0 = X row p0 + xoff
-    const long long p_begin = (long long)sp * chunk;
-    long long p_end = p_begin + chunk;
-    if (p_end > rows) p_end = rows;
-    const int iters = p_end > p_begin ? (int)((p_end - p_begin + UM_BK - 1) / UM_BK) : 0;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tma_prefetch_desc(&mYhi); tma_prefetch_desc(&mYlo); tma_prefetch_desc(&mXhi); tma_prefetch_desc(&mXlo);
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                const int p0 = (int)(p_begin + (long long)it * UM_BK);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-                const uint32_t fb = mapa_rank0(full_bar(s));
-                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    tma_load_2d_cg2(sa + j * 8192, &mYhi, fb, co0 + j * 64, p0);
-                    if (TERMS == 3) tma_load_2d_cg2(sa + Cfg::A_BYTES + j * 8192, &mYlo, fb, co0 + j * 64, p0);
-                }
-                tma_load_2d_cg2(sa + Cfg::B_OFF, &mXhi, fb, ci0, p0 + xoff);
-                if (TERMS == 3) tma_load_2d_cg2(sa + Cfg::B_OFF + Cfg::B_BYTES, &mXlo, fb, ci0, p0 + xoff);
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = umma_idesc(256, 128, 1, 1);
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-#pragma unroll
-                for (int k = 0; k < UM_BK / 16; ++k) {
-                    const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const uint32_t xrow = sa + Cfg::B_OFF + (uint32_t)(k * 16 + dx) * 128u;     // window row 16k + (1 + (dx - 1))
-                        const uint64_t x_hi = umma_desc(xrow, 8192, 1024);
-                        const uint32_t acc = tmem_base + (uint32_t)(dx * 128);
-                        if (TERMS == 3) {
-                            const uint64_t x_lo = umma_desc(xrow + Cfg::B_BYTES, 8192, 1024);
-                            tc_mma_bf16_cg2(acc, y_lo, x_hi, idesc, (it | k) != 0);
-                            tc_mma_bf16_cg2(acc, y_hi, x_lo, idesc, 1);
-                            tc_mma_bf16_cg2(acc, y_hi, x_hi, idesc, 1);
-                        } else {
-                            tc_mma_bf16_cg2(acc, y_hi, x_hi, idesc, (it | k) != 0);
-                        }
-                    }
-                }
-                tc_commit_mc2(empty_bar(s));
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
-            }
-            tc_commit_mc2(accum_bar);
-        }
-    } else {
-        const int quad = warp & 3;
-        const int co = co0 + quad * 32 + lane;
-        if (iters > 0) {
-            mbar_wait(accum_bar, 0);
-            tc_fence_after();
-        }
-#pragma unroll 1
-        for (int dx = 0; dx < 3; ++dx) {
-            const int t = dyg * 3 + dx;
-            float* dst = partial + (((size_t)sp * 9 + t) * Cout + co) * Cin + ci_pair0;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                float v[32];
-                if (iters > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(dx * 128 + c), v);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-        }
-        tc_fence_before();
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
-    }
-}
-
 // dW[co][ci][t] (OIHW) = sum_sp partial[sp*ntaps + t][co][ci]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int Cout, int Cin, int ntaps,
                                                            int nsplit, float* __restrict__ dW) {
@@ -1263,18 +1115,25 @@ static int make_map(CUtensorMap* m, const bf16* ptr, long long rows, int cols, i
     return 0;
 }
 
-static int g_num_sms = 0;
+// SM count of the current device (cached per device; concurrent first calls write the same value)
+static int g_sm_count[64] = {0};
+static int num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = g_sm_count[dev];
+    if (!n) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev] = n;
+    }
+    return n;
+}
 
 template <int BN, int FL, int TERMS>
 static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s, int nz = 1) {
     using Cfg = ConvCfg<BN, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
     if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (!g_num_sms) {
-        int dev = 0;
-        SIMQ_CUDA(cudaGetDevice(&dev));
-        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = num_sms();
     if (A.rows >= (1LL << 31) - 256) { simq_set_error("k_conv_umma: too many rows"); return 1; }
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM, Cfg::BK) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM, Cfg::BK) ||
@@ -1296,11 +1155,7 @@ static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int nta
     using Cfg = Conv2Cfg<TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
     if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2_umma_kernel<FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (!g_num_sms) {
-        int dev = 0;
-        SIMQ_CUDA(cudaGetDevice(&dev));
-        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = num_sms();
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, UM_BM) || make_map(&mAlo, A.t.lo, A.rows, A.cols, UM_BM) ||
         make_map(&mWhi, W.t.hi, W.rows, W.cols, Cfg::BN / 2) || make_map(&mWlo, W.t.lo, W.rows, W.cols, Cfg::BN / 2))
@@ -1328,11 +1183,7 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
     using Cfg = Conv2WCfg<TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
     if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2w_umma_kernel<FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (!g_num_sms) {
-        int dev = 0;
-        SIMQ_CUDA(cudaGetDevice(&dev));
-        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = num_sms();
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, WIN_ROWS) || make_map(&mAlo, A.t.lo, A.rows, A.cols, WIN_ROWS) ||
         make_map(&mWhi, W.t.hi, W.rows, W.cols, Cfg::BN / 2) || make_map(&mWlo, W.t.lo, W.rows, W.cols, Cfg::BN / 2))
@@ -1406,10 +1257,6 @@ static int conv_splitk(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
     return 0;
 }
 
-static float* g_splitk_scratch = nullptr;      // set per call by api.cu (the context's wgrad scratch, idle during forwards)
-static size_t g_splitk_floats = 0;
-void umma_set_splitk_scratch(float* p, size_t floats) { g_splitk_scratch = p; g_splitk_floats = floats; }
-
 int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     if (umma_init()) return 1;
     if (!umma_conv_supported(A.cols, N) || W.cols != A.cols || W.rows != (long long)ntaps * N) {
@@ -1417,18 +1264,14 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         return 1;
     }
     if (N == 32) return dispatch_conv<32>(A, W, N, ntaps, out, ep, s);
-    if (ntaps == 9 && !ep.stats && !ep.bn_raw && !ep.add_g && g_splitk_scratch) {
-        if (!g_num_sms) {
-            int dev = 0;
-            SIMQ_CUDA(cudaGetDevice(&dev));
-            SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        }
+    if (ntaps == 9 && !ep.stats && !ep.bn_raw && !ep.add_g && ep.splitk_scratch) {
+        const int g_num_sms = num_sms();
         const int bn = N % 128 == 0 ? 128 : 64;
         const long long tiles = (long long)ceil_div(A.rows, 128) * (N / bn);
         const int nz = tiles * 9 <= 2 * g_num_sms ? 9 : tiles * 3 <= g_num_sms ? 3 : 1;
-        if (nz > 1 && (size_t)nz * A.rows * N <= g_splitk_floats)
-            return bn == 128 ? conv_splitk<128>(A, W, N, ntaps, out, ep, nz, g_splitk_scratch, s)
-                             : conv_splitk<64>(A, W, N, ntaps, out, ep, nz, g_splitk_scratch, s);
+        if (nz > 1 && (size_t)nz * A.rows * N <= ep.splitk_floats)
+            return bn == 128 ? conv_splitk<128>(A, W, N, ntaps, out, ep, nz, ep.splitk_scratch, s)
+                             : conv_splitk<64>(A, W, N, ntaps, out, ep, nz, ep.splitk_scratch, s);
     }
     // tile policy for N % 256 == 0: the CTA-pair kernel (256 x 256 per pair) runs ~12 % more tensor work per cycle
     // than 128 x 128 single-CTA tiles but quantises worse on small problems; pick the cheaper estimate in units
@@ -1439,11 +1282,7 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         policy = !e ? 0 : !strcmp(e, "128") ? 1 : !strcmp(e, "pair") ? 3 : 0;
     }
     if (N % 256 == 0 && policy != 1) {
-        if (!g_num_sms) {
-            int dev = 0;
-            SIMQ_CUDA(cudaGetDevice(&dev));
-            SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        }
+        const int g_num_sms = num_sms();
         const long long t128 = (long long)ceil_div(A.rows, 128) * (N / 128), t256 = (long long)ceil_div(A.rows, 256) * (N / 256);
         const double cost_single = (double)((t128 + g_num_sms - 1) / g_num_sms);
         const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
@@ -1492,11 +1331,7 @@ static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, f
     using Cfg = WgradCfg<128, TERMS>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
     if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad2_umma_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (!g_num_sms) {
-        int dev = 0;
-        SIMQ_CUDA(cudaGetDevice(&dev));
-        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = num_sms();
     const int Cout = dY.cols, Cin = X.cols;
     const long long rows = dY.rows;
     CUtensorMap mYhi, mYlo, mXhi, mXlo;
@@ -1529,47 +1364,6 @@ static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, f
     return 0;
 }
 
-template <int TERMS>
-static int launch_wgrad3(const UmmaTensor& dY, const UmmaTensor& X, float* dW, float* scratch, cudaStream_t s) {
-    using Cfg = Wgrad3Cfg<TERMS>;
-    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(wgrad3_umma_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (!g_num_sms) {
-        int dev = 0;
-        SIMQ_CUDA(cudaGetDevice(&dev));
-        SIMQ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int Cout = dY.cols, Cin = X.cols;
-    const long long rows = dY.rows;
-    CUtensorMap mYhi, mYlo, mXhi, mXlo;
-    if (make_map(&mYhi, dY.t.hi, rows, Cout, UM_BK) || make_map(&mYlo, dY.t.lo, rows, Cout, UM_BK) ||
-        make_map(&mXhi, X.t.hi, rows, Cin, Cfg::XWIN_ROWS) || make_map(&mXlo, X.t.lo, rows, Cin, Cfg::XWIN_ROWS))
-        return 1;
-    const int tiles = (Cout / 256) * (Cin / 128) * 3, clusters = g_num_sms / 2;
-    long long max_split = rows / (8 * UM_BK);
-    if (max_split < 1) max_split = 1;
-    int nsplit = 1;
-    double best = -1.0;
-    for (int n = 1; n <= 64 && n <= max_split; ++n) {
-        const int work = tiles * n, rounds = (work + clusters - 1) / clusters;
-        if (rounds > 4 && best > 0) break;
-        const double eff = (double)work / ((double)rounds * clusters) - (rounds < 2 ? 0.25 : 0.0);
-        if (eff > best + 1e-9) { best = eff; nsplit = n; }
-    }
-    const size_t per_split = (size_t)9 * Cout * Cin;
-    while (nsplit > 1 && per_split * nsplit > umma_wgrad_scratch_floats()) --nsplit;
-    if (per_split * nsplit > umma_wgrad_scratch_floats()) { simq_set_error("wgrad scratch too small"); return 1; }
-    long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
-    dim3 grid(2 * (Cout / 256), Cin / 128, 3 * nsplit);
-    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * 9, s);
-    wgrad3_umma_kernel<TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, nsplit, chunk, scratch);
-    SIMQ_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<ceil_div((long long)per_split, 256), 256, 0, s>>>(scratch, Cout, Cin, 9, nsplit, dW);
-    prof_mark(PROF_WGRAD, false, 0, s);
-    SIMQ_LAUNCH_CHECK();
-    return 0;
-}
-
 int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, int terms, cudaStream_t s) {
     if (umma_init()) return 1;
     if (!umma_wgrad_supported(dY.cols, X.cols) || dY.rows != X.rows) {
@@ -1578,10 +1372,6 @@ int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW
     }
     static int pair = -1;
     if (pair < 0) { const char* e = getenv("SIMQ_WGRAD_PAIR"); pair = e ? atoi(e) : 1; }
-    static int window = -1;
-    if (window < 0) { const char* e = getenv("SIMQ_WGRAD_WINDOW"); window = e ? atoi(e) : 0; }
-    if (pair && window && ntaps == 9 && dY.cols % 256 == 0 && X.cols % 256 == 0)
-        return terms == 1 ? launch_wgrad3<1>(dY, X, dW, scratch, s) : launch_wgrad3<3>(dY, X, dW, scratch, s);
     if (pair && dY.cols % 256 == 0 && X.cols % 256 == 0)
         return terms == 1 ? launch_wgrad2<1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad2<3>(dY, X, ntaps, dW, scratch, s);
     if (X.cols % 128 == 0)

@@ -30,7 +30,8 @@ int k_head_up2(const float* t, int B, int A, const float* b3, float* q, cudaStre
 // ---- DQN tail / optimiser ----
 int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const long long* action, const float* reward,
                const unsigned char* nonfinal, float gamma, int B, int Bn, int A, int double_dqn, float* per_sample,
-               long long* best_action, float* out2, float* dq, cudaStream_t s);
+               long long* best_action, float* out2, float* dq, int* err_flag, cudaStream_t s);
+#define SIMQ_DEVERR_ACTION_RANGE 1   // bit of the context's device error word: an action index outside [0, A*96*96)
 int k_bce_tail(const float* q, const float* target, long long tstride, long long n, float* out1, float* dq, double* partials,
                cudaStream_t s);
 int k_gather_rows(const float* src, const long long* idx, int n, long long row_floats, float* dst, cudaStream_t s);
@@ -95,12 +96,15 @@ struct ConvEpilogue {
     // stats rows become (sum dz, sum dz * (bn_raw - mean) * invstd) -- saves the separate reduction pass
     const float* bn_raw; const bf16* bn_mask; const float* bn_mean; const float* bn_invstd;
     int terms;                // 3: split-bf16 parity mode (lo*hi + hi*lo + hi*hi); 1: bf16 fast mode (hi*hi only)
+    // scratch the split-K path of small problems may use (NULL disables it): per call, so that two contexts on two threads never share it
+    float* splitk_scratch; size_t splitk_floats;
 };
 static inline ConvEpilogue conv_ep(int pitch25) {
     ConvEpilogue e;
     e.pitch25 = pitch25; e.add_prev = nullptr; e.add_g = nullptr; e.add_g_mask = nullptr; e.scale = nullptr; e.shift = nullptr;
     e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
     e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr; e.terms = 3;
+    e.splitk_scratch = nullptr; e.splitk_floats = 0;
     return e;
 }
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
@@ -125,7 +129,6 @@ struct UmmaTensor {          // a split tensor plus its row count / width, enoug
 int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s);
 int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW, float* scratch, int terms, cudaStream_t s);
 int umma_init();             // resolves cuTensorMapEncodeTiled
-void umma_set_splitk_scratch(float* p, size_t floats);   // scratch for the split-K path of small convs (NULL disables it)
 bool umma_conv_supported(int K, int N);
 int umma_conv_m_tiles(long long rows);     // rows of ConvEpilogue::stats written by k_conv_umma
 bool umma_wgrad_supported(int Cout, int Cin);

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256) dqn_tail_kernel(const float* __restrict__
                                                        const float* __restrict__ reward, const unsigned char* __restrict__ nonfinal,
                                                        float gamma, int B, long long row_len, int double_dqn,
                                                        float* __restrict__ per_sample, long long* __restrict__ best_action,
-                                                       float* __restrict__ dq) {
+                                                       float* __restrict__ dq, int* __restrict__ err_flag) {
     const int i = blockIdx.x;
     float next_v = 0.f;                                   // train.py:116
     if (nonfinal[i]) {
@@ -448,6 +448,11 @@ __global__ void __launch_bounds__(256) dqn_tail_kernel(const float* __restrict__
     }
     if (threadIdx.x == 0) {
         long long a = action[i];
+        if (a < 0 || a >= row_len) {                      // the reference's gather would raise: report, never index out of bounds
+            if (err_flag) atomicOr(err_flag, SIMQ_DEVERR_ACTION_RANGE);
+            per_sample[i * 2 + 0] = per_sample[i * 2 + 1] = __int_as_float(0x7fc00000);      // NaN loss / td_error
+            return;
+        }
         float q = q_s[(size_t)i * row_len + a];           // train.py:115
         float y = reward[i] + gamma * next_v;             // train.py:126
         float d = q - y, ad = fabsf(d);
@@ -468,12 +473,12 @@ __global__ void dqn_tail_finalize_kernel(const float* __restrict__ per_sample, i
 
 int k_dqn_tail(const float* q_s, const float* q_no, const float* q_nt, const long long* action, const float* reward,
                const unsigned char* nonfinal, float gamma, int B, int Bn, int A, int double_dqn, float* per_sample,
-               long long* best_action, float* out2, float* dq, cudaStream_t s) {
+               long long* best_action, float* out2, float* dq, int* err_flag, cudaStream_t s) {
     long long row_len = (long long)A * 9216;
     (void)Bn;
     if (dq) { SIMQ_CUDA(cudaMemsetAsync(dq, 0, sizeof(float) * (size_t)B * row_len, s)); }
     dqn_tail_kernel<<<B, 256, 0, s>>>(q_s, q_no, q_nt, action, reward, nonfinal, gamma, B, row_len, double_dqn,
-                                      per_sample, best_action, dq);
+                                      per_sample, best_action, dq, err_flag);
     SIMQ_LAUNCH_CHECK();
     dqn_tail_finalize_kernel<<<1, 32, 0, s>>>(per_sample, B, out2);
     SIMQ_LAUNCH_CHECK();

@@ -293,7 +293,10 @@ def train(cfg, policy_net, target_net, optimizer, batch, transform_fn, discount_
     policies.py:44-45, which the stem kernel absorbs)."""
     db = _enqueue_train(cfg, policy_net, target_net, optimizer, batch, discount_factor)
     torch.cuda.current_stream().synchronize()       # the reference syncs here too: two .item() calls (train.py:138-139)
-    return {'td_error': float(db.out2_host[1]), 'loss': float(db.out2_host[0])}
+    loss = float(db.out2_host[0])
+    if loss != loss:                                # NaN: an input error only the device could see (e.g. an action out of range)?
+        _lib.check(_lib.lib().simq_check_device_errors(_unwrap(policy_net).ctx().handle, _lib.stream_ptr()), 'simq_train_step')
+    return {'td_error': float(db.out2_host[1]), 'loss': loss}
 
 
 def train_groups(cfg, policy, target_nets, optimizers, batches, optimizers_intention=None):

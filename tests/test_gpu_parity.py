@@ -500,3 +500,42 @@ def test_full_size_properties_b128():
     assert np.isfinite(info['loss']) and np.isfinite(info['td_error'])
     assert torch.isfinite(net.flat_params).all() and not torch.equal(before, net.flat_params)
     assert int(net.bn1.num_batches_tracked) == 3 + 2
+
+
+def test_out_of_range_action_is_reported_not_indexed():
+    """train.py:115 gathers Q(s, a): an action index outside [0, A*96*96) raises in the reference.  Here the tail kernel must
+    not index out of bounds: it flags the context's device error word, the step reports NaN, and train.train raises."""
+    from spatial_intention_maps_b200 import _lib, networks, synth, train as T
+    net, st = G.make_net(4, 2, 3, max_batch=4)
+    tgt = networks.FCN(4, 2, max_batch=4)
+    tgt.load_state_dict(st)
+    tgt = tgt.to(G.DEV).eval()
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    good = synth.synth_batch(4, 4, 2, 3, terminal_every=2)
+    bad = good._replace(action=(good.action[0], 2 * 9216, good.action[2], -1))
+    with pytest.raises(_lib.SimqError, match='action index'):
+        T.train(G.Cfg(4, 4), net, tgt, opt, bad, None, 0.75)
+    info = T.train(G.Cfg(4, 4), net, tgt, opt, good, None, 0.75)          # the context stays usable, the flag was cleared
+    assert np.isfinite(info['loss'])
+
+
+def test_deepcopy_target_network_idiom():
+    """``target = copy.deepcopy(policy_net)`` (the common PyTorch DQN idiom): the copy computes the same Q-map from its own flat
+    vectors / context, and keeps computing the OLD Q-map after the original has been updated."""
+    import copy
+    from spatial_intention_maps_b200 import synth
+    net, _ = G.make_net(4, 2, 9, max_batch=2)
+    x = torch.from_numpy(synth.synth_states(2, 4, 9)).to(G.DEV).permute(0, 3, 1, 2)
+    net.eval()
+    with torch.no_grad():
+        q0 = net(x)
+        cp = copy.deepcopy(net)
+        assert torch.equal(cp(x), q0)
+        for p in net.parameters():
+            p.mul_(0.5)
+        assert not torch.equal(net(x), q0) and torch.equal(cp(x), q0)
+        for p in cp.parameters():                      # a write through .data is invisible to the version counters ...
+            p.data.mul_(0.5)
+        cp.mark_params_changed()                       # ... so the caller says so (Polyak-style updates)
+        assert torch.equal(cp(x), net(x))
