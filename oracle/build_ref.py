@@ -2,7 +2,7 @@
 INFRASTRUCTURE ONLY (never imported by the product package).
 
 The reference is Python: its "build" is byte-compilation.  This recipe compiles the four modules of the path -- where they lie
-under /root/reference -- to sourceless ``oracle/_ref/<module>.pyc`` files (outputs only; no reference source enters the
+under /root/reference -- to sourceless byte-code files ``oracle/_ref/<module>.bc`` (the .pyc format under a suffix that repository snapshots do not strip) (outputs only; no reference source enters the
 repository; ``oracle/_ref/`` is git-ignored but NOT gpurun-ignored, so it travels to the GPU box like our own built ``.so``).
 ``oracle/ref_runner.py`` imports them with ``envs`` / ``utils`` stubbed (pybullet & co. are not installed)
 and drives ``train.train`` unmodified.  Run by ``__graft_entry__.build()`` when /root/reference is present.
@@ -26,11 +26,11 @@ def build(verbose=True) -> bool:
     out = os.path.join(HERE, '_ref')
     os.makedirs(out, exist_ok=True)
     for m in MODULES:
-        py_compile.compile(os.path.join(REF, m + '.py'), cfile=os.path.join(out, m + '.pyc'), doraise=True, optimize=0)
+        py_compile.compile(os.path.join(REF, m + '.py'), cfile=os.path.join(out, m + '.bc'), doraise=True, optimize=0)
     with open(os.path.join(out, 'BUILD_INFO'), 'w') as f:
         f.write(f'python {sys.version.split()[0]}; byte-compiled from {REF}: ' + ', '.join(m + '.py' for m in MODULES) + '\n')
     if verbose:
-        print('staged', ', '.join(m + '.pyc' for m in MODULES), 'into', out)
+        print('staged', ', '.join(m + '.bc' for m in MODULES), 'into', out)
     return True
 
 

@@ -1,4 +1,4 @@
-"""Drives the staged reference (``oracle/_ref/*.pyc``, see ``oracle/build_ref.py``) for bench.py's reference arm and same-GPU
+"""Drives the staged reference (``oracle/_ref/*.bc``, see ``oracle/build_ref.py``) for bench.py's reference arm and same-GPU
 comparator.  TEST / MEASUREMENT INFRASTRUCTURE ONLY.
 
 ``train.train`` (train.py:108-141), ``policies.DQNPolicy`` (policies.py:11-74) and ``networks.FCN`` (networks.py:6-26) run
@@ -19,7 +19,7 @@ REF_DIR = os.path.join(HERE, '_ref')
 
 
 def available() -> bool:
-    return all(os.path.exists(os.path.join(REF_DIR, m + '.pyc')) for m in ('networks', 'resnet', 'policies', 'train'))
+    return all(os.path.exists(os.path.join(REF_DIR, m + '.bc')) for m in ('networks', 'resnet', 'policies', 'train'))
 
 
 _mods = None
@@ -53,17 +53,23 @@ def load():
     sys.modules['utils'] = types.ModuleType('utils')
     for k in ('networks', 'resnet', 'policies', 'train'):
         sys.modules.pop(k, None)
-    sys.path.insert(0, REF_DIR)
+    import importlib.machinery
+    import importlib.util
+    mods = {}
     try:
-        import networks, policies, train          # noqa: E401  (sourceless .pyc imports from oracle/_ref)
+        for name in ('resnet', 'networks', 'policies', 'train'):          # import order = dependency order (networks.py:4, policies.py:7)
+            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_DIR, name + '.bc'))
+            mod = importlib.util.module_from_spec(importlib.util.spec_from_loader(name, loader))
+            sys.modules[name] = mod
+            loader.exec_module(mod)
+            mods[name] = mod
     finally:
-        sys.path.remove(REF_DIR)
         for k, v in saved.items():                # do not leave the reference's top-level names in sys.modules
             if v is not None:
                 sys.modules[k] = v
             else:
                 sys.modules.pop(k, None)
-    _mods = (networks, policies, train)
+    _mods = (mods['networks'], mods['policies'], mods['train'])
     return _mods
 
 

@@ -135,6 +135,7 @@ struct PackedSet {                   // split-bf16 shadows of the conv weights o
 struct simq_ctx {
     int device, maxB, backend;
     int terms;                       // 3 = parity mode (default), 1 = bf16 fast mode (simq_set_precision)
+    int terms_dgrad, terms_wgrad;    // backward GEMMs: = terms, or 2 (dy contributes its hi plane only; simq_set_backward_terms)
     NetDesc d;
     char* pool; size_t pool_bytes, pool_used;
     ActSet set[3];                   // 0: saved (differentiated forward), 1: scratch (no-grad forwards), 2: eval-only (concurrent target pass)
@@ -284,7 +285,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     SIMQ_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { simq_set_error("simq_ctx_create: device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor); return 2; }
     simq_ctx* c = new simq_ctx();
-    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = 3;
+    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = c->terms_dgrad = c->terms_wgrad = 3;
     build_desc(c->d, C, A);
     c->pool = nullptr;
     carve_all(c, true);
@@ -355,8 +356,15 @@ extern "C" int simq_set_backend(simq_ctx* c, int backend) {
 }
 extern "C" int simq_set_precision(simq_ctx* c, int mode) {
     if (!c || (mode != SIMQ_PRECISION_PARITY && mode != SIMQ_PRECISION_BF16)) { simq_set_error("simq_set_precision: bad argument"); return 1; }
-    c->terms = mode == SIMQ_PRECISION_BF16 ? 1 : 3;
+    c->terms = c->terms_dgrad = c->terms_wgrad = mode == SIMQ_PRECISION_BF16 ? 1 : 3;
     ++c->pack_epoch;                 // invalidates captured graphs (the key carries pack_epoch)
+    return 0;
+}
+extern "C" int simq_set_backward_terms(simq_ctx* c, int dgrad_terms, int wgrad_terms) {
+    if (!c || (dgrad_terms != 2 && dgrad_terms != 3) || (wgrad_terms != 2 && wgrad_terms != 3)) { simq_set_error("simq_set_backward_terms: terms must be 2 or 3"); return 1; }
+    if (c->terms != 3) { simq_set_error("simq_set_backward_terms: only meaningful in parity mode"); return 1; }
+    c->terms_dgrad = dgrad_terms; c->terms_wgrad = wgrad_terms;
+    ++c->pack_epoch;
     return 0;
 }
 extern "C" size_t simq_workspace_bytes(const simq_ctx* c) { return c ? c->pool_bytes : 0; }
@@ -429,10 +437,10 @@ extern "C" int simq_set_schedule(simq_ctx* c, int mode) {
 }
 
 static int conv_any(simq_ctx* c, int backend, Split A, long long rows, int K, Split W, int N, int ntaps, float* out,
-                    ConvEpilogue ep, const Lane& L) {
+                    ConvEpilogue ep, const Lane& L, int terms = 0 /* 0: the context's forward precision */) {
     if (backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
         UmmaTensor a{A, rows, K}, w{W, (long long)ntaps * N, K};
-        ep.terms = c->terms;
+        ep.terms = terms ? terms : c->terms;
         // the lane's scratch is idle whenever one of its forward convs / dgrads runs: lend it to the split-K path of small problems
         if (out != L.scratch) { ep.splitk_scratch = L.scratch; ep.splitk_floats = umma_wgrad_scratch_floats(); }
         return k_conv_umma(a, w, N, ntaps, out, ep, L.s);
@@ -443,7 +451,7 @@ static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows
                      const Lane& L) {
     if (backend == SIMQ_BACKEND_UMMA && umma_wgrad_supported(Cout, Cin)) {
         UmmaTensor y{dY, rows, Cout}, x{X, rows, Cin};
-        return k_wgrad_umma(y, x, ntaps, dW, L.scratch, c->terms, L.s);
+        return k_wgrad_umma(y, x, ntaps, dW, L.scratch, c->terms_wgrad, L.s);
     }
     return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, L.scratch, L.s);
 }
@@ -677,7 +685,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     TRY(bias_grad(c, c->dy2h, R48, HEAD2_DY_STRIDE, c->sums, M));
     SIMQ_CUDA(cudaMemcpyAsync(grads + d.poff[d.h2_bias], c->sums, sizeof(float) * 32, cudaMemcpyDeviceToDevice, s));
     ConvEpilogue ep0 = conv_ep(0);
-    TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M));
+    TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M, c->terms_dgrad));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     float* G = c->G[0];
     float* Gn = c->G[1];
@@ -703,7 +711,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     int g_parts = 0;                 // partial rows already available for the BN consuming G
     {
         ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
-        TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M));
+        TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M, c->terms_dgrad));
         g_parts = e.bn_raw ? nparts_fused : 0;
     }
     { float* t = G; G = Gn; Gn = t; }
@@ -721,7 +729,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         TRY(wgrad_on_w(cur, dyA[cur], Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w]));
         if (P.has_ds) TRY(wgrad_on_w(BUF_B, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w]));
         ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
-        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M, c->terms_dgrad));
         // b1 = relu(bn1(raw1))
         cur ^= 1; TRY(acquire(cur));
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
@@ -736,7 +744,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
             ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
             g_parts = ep.bn_raw ? nparts_fused : 0;
         }
-        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M, c->terms_dgrad));
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
@@ -744,7 +752,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                 epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
                 g_parts = epd.bn_raw ? nparts_fused : 0;
             }
-            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M));
+            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M, c->terms_dgrad));
         }
         { float* t = G; G = Gn; Gn = t; }
     }
@@ -1133,7 +1141,7 @@ extern "C" int simq_test_conv(simq_ctx* c, int backend, int mode, int B, int Cin
     } else if (mode == 1) {
         TRY(k_import_p25(a, B, Cout, Y, nullptr, s));
         TRY(k_pack_weights(w, Cout, Cin, taps, wf, wb, s));
-        TRY(conv_any(c, backend, Y, R25, Cout, wb, Cin, taps, c->G[0], ep25, main_lane(c, s)));
+        TRY(conv_any(c, backend, Y, R25, Cout, wb, Cin, taps, c->G[0], ep25, main_lane(c, s), c->terms_dgrad));
         return k_export_p25(c->G[0], none, B, Cin, out, s);
     } else {
         TRY(k_import_p25(a, B, Cin, X, nullptr, s));

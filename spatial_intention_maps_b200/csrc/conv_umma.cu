@@ -134,6 +134,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // and dropped: no gain over these tiles; large-N layers use the CTA-pair kernel instead.)
 // TERMS = 3: split-bf16 operands, lo*hi + hi*lo + hi*hi (parity mode).  TERMS = 1: hi planes only, one MMA per
 // product (plain bf16 "fast" mode: ~3x less tensor work, fails the 1e-3 Q-map bar -- opt-in, see simq_set_precision).
+// TERMS = 2 (backward GEMMs only, opt-in): the A operand -- the output gradient dy -- contributes its hi plane only,
+// the other operand stays split: hi*lo + hi*hi, two MMAs per product and no dy.lo loads (gradients carry no parity bar in
+// the north_star; the Q-map / arg-max path never uses it).
 template <int BN, int TERMS = 3>
 struct ConvCfg {
     static constexpr int BK = 64;
@@ -141,9 +144,10 @@ struct ConvCfg {
     static constexpr int W_BYTES = BN * BK * 2;               // one plane of the W tile
     static constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;    // SmemDescriptor layout_type
     static constexpr uint32_t SBO = BK == 64 ? 1024u : 512u;  // 8 rows of BK*2 bytes
-    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
-    static constexpr int W_OFF = PLANES * A_BYTES;            // stage layout: A hi [, A lo], W hi [, W lo]
-    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+    static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_PLANES = TERMS >= 2 ? 2 : 1;
+    static constexpr int W_OFF = A_PLANES * A_BYTES;          // stage layout: A hi [, A lo], W hi [, W lo]
+    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + W_PLANES * W_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4; // per epilogue warp: 32 rows x 32 columns fp32
     static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -354,10 +358,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     const int arow = m0 + off;
                     tma_load_2d(sa, &mAhi, full_bar(s), kc * BK, arow);
                     tma_load_2d(sa + Cfg::W_OFF, &mWhi, full_bar(s), kc * BK, t * N + n0);
-                    if (TERMS == 3) {
-                        tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * BK, arow);
-                        tma_load_2d(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, full_bar(s), kc * BK, t * N + n0);
-                    }
+                    if (TERMS == 3) tma_load_2d(sa + Cfg::A_BYTES, &mAlo, full_bar(s), kc * BK, arow);
+                    if (TERMS >= 2) tma_load_2d(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, full_bar(s), kc * BK, t * N + n0);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -384,6 +386,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                             const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
                             tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
                             tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else if (TERMS == 2) {
+                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                            tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
                             tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
                         } else {
                             tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
@@ -460,13 +466,14 @@ struct Conv2Cfg {
     static constexpr int BN = 256;                            // pair tile: 256 rows x 256 columns
     static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // this CTA's 128 A rows, one plane (16 KB)
     static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of the W tile, one plane (16 KB)
-    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
-    static constexpr int W_OFF = PLANES * A_BYTES;
-    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+    static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_PLANES = TERMS >= 2 ? 2 : 1;
+    static constexpr int W_OFF = A_PLANES * A_BYTES;
+    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + W_PLANES * W_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
     static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
-    static constexpr int STAGES = TERMS == 3 ? 3 : 6;
+    static constexpr int STAGES = TERMS == 3 ? 3 : TERMS == 2 ? 4 : 6;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
     static constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
 };
@@ -529,10 +536,8 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
                     tma_load_2d_cg2(sa, &mAhi, fb, kc * UM_BK, m0 + off);
                     tma_load_2d_cg2(sa + Cfg::W_OFF, &mWhi, fb, kc * UM_BK, t * N + wn0);
-                    if (TERMS == 3) {
-                        tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 + off);
-                        tma_load_2d_cg2(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
-                    }
+                    if (TERMS == 3) tma_load_2d_cg2(sa + Cfg::A_BYTES, &mAlo, fb, kc * UM_BK, m0 + off);
+                    if (TERMS >= 2) tma_load_2d_cg2(sa + Cfg::W_OFF + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -559,6 +564,10 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                             const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, 1024);
                             tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else if (TERMS == 2) {
+                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, 1024);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
                         } else {
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
@@ -614,11 +623,12 @@ struct Conv2WCfg {
     static constexpr int BN = 256;
     static constexpr int A_BYTES = WIN_ROWS * UM_BK * 2;      // one plane of this CTA's window (23 KB)
     static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of one W tile, one plane (16 KB)
-    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_PLANES = TERMS >= 2 ? 2 : 1;
     static constexpr int A_BUFS = 2;
-    static constexpr int A_BUF_BYTES = PLANES * A_BYTES;
-    static constexpr int W_STAGE_BYTES = PLANES * W_BYTES;
-    static constexpr int W_STAGES = TERMS == 3 ? 3 : 6;
+    static constexpr int A_BUF_BYTES = A_PLANES * A_BYTES;
+    static constexpr int W_STAGE_BYTES = W_PLANES * W_BYTES;
+    static constexpr int W_STAGES = TERMS == 3 ? 3 : TERMS == 2 ? 4 : 6;
     static constexpr int W_BASE = A_BUFS * A_BUF_BYTES;
     static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
@@ -703,7 +713,7 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                     const uint32_t fb = mapa_rank0(wfull_bar(s));
                     const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
                     tma_load_2d_cg2(sw, &mWhi, fb, kc * UM_BK, t * N + wn0);
-                    if (TERMS == 3) tma_load_2d_cg2(sw + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
+                    if (TERMS >= 2) tma_load_2d_cg2(sw + Cfg::W_BYTES, &mWlo, fb, kc * UM_BK, t * N + wn0);
                     if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -739,6 +749,10 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                             const uint64_t w_lo = umma_desc(sw + Cfg::W_BYTES + k * 32, 16, 1024);
                             tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, accumulate);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                        } else if (TERMS == 2) {
+                            const uint64_t w_lo = umma_desc(sw + Cfg::W_BYTES + k * 32, 16, 1024);
+                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, accumulate);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
                         } else {
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, accumulate);
@@ -781,9 +795,10 @@ template <int BN, int TERMS = 3>
 struct WgradCfg {
     static constexpr int A_BYTES = UM_BM * UM_BK * 2;         // dY plane: 2 blocks of [64 rows][64 co]
     static constexpr int B_BYTES = BN * UM_BK * 2;            // X plane: BN/64 blocks of [64 rows][64 ci]
-    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
-    static constexpr int B_OFF = PLANES * A_BYTES;            // stage layout: dY hi [, dY lo], X hi [, X lo]
-    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;       // TERMS = 2: dY contributes its hi plane only
+    static constexpr int B_PLANES = TERMS >= 2 ? 2 : 1;
+    static constexpr int B_OFF = A_PLANES * A_BYTES;          // stage layout: dY hi [, dY lo], X hi [, X lo]
+    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + B_PLANES * B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
@@ -840,7 +855,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) {
                     tma_load_2d(sa + Cfg::B_OFF + j * 8192, &mXhi, full_bar(s), ci0 + j * 64, p0 + off);
-                    if (TERMS == 3) tma_load_2d(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, full_bar(s), ci0 + j * 64, p0 + off);
+                    if (TERMS >= 2) tma_load_2d(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, full_bar(s), ci0 + j * 64, p0 + off);
                 }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
@@ -864,6 +879,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
                         const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
                         tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
                         tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
+                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                    } else if (TERMS == 2) {
+                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                        tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
                         tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
                     } else {
                         tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
@@ -963,10 +982,8 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
                 for (int j = 0; j < 2; ++j) {
                     tma_load_2d_cg2(sa + j * 8192, &mYhi, fb, co0 + j * 64, p0);
                     tma_load_2d_cg2(sa + Cfg::B_OFF + j * 8192, &mXhi, fb, ci0 + j * 64, p0 + off);
-                    if (TERMS == 3) {
-                        tma_load_2d_cg2(sa + Cfg::A_BYTES + j * 8192, &mYlo, fb, co0 + j * 64, p0);
-                        tma_load_2d_cg2(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, fb, ci0 + j * 64, p0 + off);
-                    }
+                    if (TERMS == 3) tma_load_2d_cg2(sa + Cfg::A_BYTES + j * 8192, &mYlo, fb, co0 + j * 64, p0);
+                    if (TERMS >= 2) tma_load_2d_cg2(sa + Cfg::B_OFF + Cfg::B_BYTES + j * 8192, &mXlo, fb, ci0 + j * 64, p0 + off);
                 }
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
@@ -988,6 +1005,10 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
                         const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
                         tc_mma_bf16_cg2(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
                         tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, 1);
+                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
+                    } else if (TERMS == 2) {
+                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                        tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
                         tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
                     } else {
                         tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
@@ -1201,6 +1222,28 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
 }
 
 // the epilogue variants the network uses
+template <int BN, bool PAIR, int F, int TERMS>
+static int conv_launch_t(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    if constexpr (PAIR) {
+        if (ntaps == 9 && conv_window_mode() != 0) return launch_conv2w<F, TERMS>(A, W, N, out, ep, s);
+        return launch_conv2<F, TERMS>(A, W, N, ntaps, out, ep, s);
+    } else {
+        return launch_conv<BN, F, TERMS>(A, W, N, ntaps, out, ep, s);
+    }
+}
+template <int BN, bool PAIR, int F>
+static int conv_by_terms(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
+    // the two-term variant exists for the epilogues dgrad launches use (raw fp32 output, +previous gradient, +masked identity
+    // gradient, +BatchNorm-backward sums): the forward never runs it
+    constexpr bool DGRAD_EPILOGUE = (F & ~(EF_PREV | EF_G | EF_BNBWD)) == EF_F32;
+    if (ep.terms == 1) return conv_launch_t<BN, PAIR, F, 1>(A, W, N, ntaps, out, ep, s);
+    if (ep.terms == 2) {
+        if constexpr (DGRAD_EPILOGUE) return conv_launch_t<BN, PAIR, F, 2>(A, W, N, ntaps, out, ep, s);
+        simq_set_error("k_conv_umma: two-term operands are a backward-only mode (epilogue 0x%x)", F);
+        return 1;
+    }
+    return conv_launch_t<BN, PAIR, F, 3>(A, W, N, ntaps, out, ep, s);
+}
 template <int BN, bool PAIR = false>
 static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     int fl = 0;
@@ -1214,14 +1257,7 @@ static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     if (ep.out_split.hi) fl |= EF_SPLIT;
     if (ep.bn_raw) fl |= EF_BNBWD;
     switch (fl) {
-#define CASE(F) case (F):                                                                                                   \
-        if constexpr (PAIR) {                                                                                               \
-            if (ntaps == 9 && conv_window_mode() != 0)                                                                      \
-                return ep.terms == 1 ? launch_conv2w<(F), 1>(A, W, N, out, ep, s) : launch_conv2w<(F), 3>(A, W, N, out, ep, s); \
-            return ep.terms == 1 ? launch_conv2<(F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv2<(F), 3>(A, W, N, ntaps, out, ep, s); \
-        } else {                                                                                                            \
-            return ep.terms == 1 ? launch_conv<BN, (F), 1>(A, W, N, ntaps, out, ep, s) : launch_conv<BN, (F), 3>(A, W, N, ntaps, out, ep, s); \
-        }
+#define CASE(F) case (F): return conv_by_terms<BN, PAIR, (F)>(A, W, N, ntaps, out, ep, s);
         CASE(EF_F32);                                               // raw conv output (dgrad, eval head)
         CASE(EF_F32 | EF_STATS);                                    // train forward: raw + BN statistics
         CASE(EF_F32 | EF_PREV);                                     // dgrad accumulate (downsample branch)
@@ -1249,7 +1285,9 @@ static int conv_splitk(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
                        cudaStream_t s) {
     ConvEpilogue raw = conv_ep(0);
     raw.terms = ep.terms;
-    int rc = ep.terms == 1 ? launch_conv<BN, EF_F32, 1>(A, W, N, ntaps, scratch, raw, s, nz) : launch_conv<BN, EF_F32, 3>(A, W, N, ntaps, scratch, raw, s, nz);
+    int rc = ep.terms == 1 ? launch_conv<BN, EF_F32, 1>(A, W, N, ntaps, scratch, raw, s, nz)
+           : ep.terms == 2 ? launch_conv<BN, EF_F32, 2>(A, W, N, ntaps, scratch, raw, s, nz)
+                           : launch_conv<BN, EF_F32, 3>(A, W, N, ntaps, scratch, raw, s, nz);
     if (rc) return rc;
     const long long n = A.rows * (N / 4);
     splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scratch, nz, (int)A.rows, N, ep, out);
@@ -1373,8 +1411,11 @@ int k_wgrad_umma(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, float* dW
     static int pair = -1;
     if (pair < 0) { const char* e = getenv("SIMQ_WGRAD_PAIR"); pair = e ? atoi(e) : 1; }
     if (pair && dY.cols % 256 == 0 && X.cols % 256 == 0)
-        return terms == 1 ? launch_wgrad2<1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad2<3>(dY, X, ntaps, dW, scratch, s);
+        return terms == 1 ? launch_wgrad2<1>(dY, X, ntaps, dW, scratch, s) : terms == 2 ? launch_wgrad2<2>(dY, X, ntaps, dW, scratch, s)
+                                                                                        : launch_wgrad2<3>(dY, X, ntaps, dW, scratch, s);
     if (X.cols % 128 == 0)
-        return terms == 1 ? launch_wgrad<128, 1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad<128, 3>(dY, X, ntaps, dW, scratch, s);
-    return terms == 1 ? launch_wgrad<64, 1>(dY, X, ntaps, dW, scratch, s) : launch_wgrad<64, 3>(dY, X, ntaps, dW, scratch, s);
+        return terms == 1 ? launch_wgrad<128, 1>(dY, X, ntaps, dW, scratch, s) : terms == 2 ? launch_wgrad<128, 2>(dY, X, ntaps, dW, scratch, s)
+                                                                                            : launch_wgrad<128, 3>(dY, X, ntaps, dW, scratch, s);
+    return terms == 1 ? launch_wgrad<64, 1>(dY, X, ntaps, dW, scratch, s) : terms == 2 ? launch_wgrad<64, 2>(dY, X, ntaps, dW, scratch, s)
+                                                                                       : launch_wgrad<64, 3>(dY, X, ntaps, dW, scratch, s);
 }

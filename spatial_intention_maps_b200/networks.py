@@ -222,6 +222,8 @@ class FCN(nn.Module):
                 _lib.check(_lib.lib().simq_set_precision(self._ctx.handle, self._precision), 'simq_set_precision')
             if getattr(self, '_schedule', None) is not None:
                 _lib.check(_lib.lib().simq_set_schedule(self._ctx.handle, self._schedule), 'simq_set_schedule')
+            if getattr(self, '_bwd_terms', None) is not None:
+                _lib.check(_lib.lib().simq_set_backward_terms(self._ctx.handle, *self._bwd_terms), 'simq_set_backward_terms')
         return self._ctx
 
     def set_backend(self, backend: int):
@@ -234,6 +236,12 @@ class FCN(nn.Module):
         m = {'parity': _lib.PRECISION_PARITY, 'bf16': _lib.PRECISION_BF16}[mode]
         self._precision = m
         _lib.check(_lib.lib().simq_set_precision(self.ctx().handle, m), 'simq_set_precision')
+
+    def set_backward_terms(self, dgrad: int = 3, wgrad: int = 3):
+        """Operand terms of the backward GEMMs (3 = default split-bf16 scheme; 2 = the output gradient contributes its bf16 hi
+        plane only: 2 MMAs per product).  The forward passes -- Q-map and arg-max parity -- are unaffected."""
+        self._bwd_terms = (int(dgrad), int(wgrad))
+        _lib.check(_lib.lib().simq_set_backward_terms(self.ctx().handle, *self._bwd_terms), 'simq_set_backward_terms')
 
     def set_schedule(self, mode: str):
         """'lanes' (default: independent pieces of a step on two streams / graph branches) or 'serial' (one stream, the

@@ -190,7 +190,9 @@ def gen_steps_clip():
     gradients AFTER the in-place rescale, ``_grad_norm`` their norm (= the max-norm when the clip is active)."""
     out = {}
     for key, clip in (('clip1', 1.0), ('clip5', 5.0), ('clipnone', None)):
-        C, rt, A, B, gamma, nsteps, seed, te = 4, 'lifting_robot', 2, 16, 0.75, 2, 16, 8
+        # (seed 11 = the c1 batch: its gradient is known to be well conditioned at B=16 -- with 16 one-hot dL/dQ entries a single ReLU
+        # flip near an output pixel can move the gradient norm by 0.5 %, which would mask what this case is about: the clip)
+        C, rt, A, B, gamma, nsteps, seed, te = 4, 'lifting_robot', 2, 16, 0.75, 2, 11, 8
         infos, grads, after, mom = run_ref_steps(C, rt, A, B, gamma, nsteps, seed, te, clip)
         pack_step(key, out, infos, grads, after, mom, C, A)
         out[key + '_cfg'] = np.array([C, A, B, nsteps, seed, te], dtype=np.int64)
