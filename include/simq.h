@@ -67,10 +67,11 @@ int simq_set_precision(simq_ctx*, int mode);
 int simq_set_schedule(simq_ctx*, int mode);
 /* Operand terms of the BACKWARD GEMMs in parity mode (default 3, 3 = the forward's split-bf16 scheme).  2: the output
  * gradient dy contributes only its bf16 hi plane (hi*lo + hi*hi: two MMAs per product and no dy.lo loads) -- dgrad_terms for
- * the input-gradient convolutions (their rounding propagates down the chain), wgrad_terms for the weight-gradient GEMMs
- * (80 000-term sums: the rounding averages out).  The forward passes -- everything the Q-map / arg-max parity bar covers -- are
+ * the input-gradient convolutions of the residual blocks with at least dgrad2_min_planes planes (their rounding propagates down
+ * the chain; the head's 1x1 convs always keep 3), wgrad_terms for the weight-gradient GEMMs (80 000-term sums: the rounding
+ * averages out).  The forward passes -- everything the Q-map / arg-max parity bar covers -- are
  * never affected.  Opt-in; see DESIGN.md for the measured gradient error against the float64 twin. */
-int simq_set_backward_terms(simq_ctx*, int dgrad_terms, int wgrad_terms);
+int simq_set_backward_terms(simq_ctx*, int dgrad_terms, int wgrad_terms, int dgrad2_min_planes);
 size_t simq_workspace_bytes(const simq_ctx*);
 
 /* Replaces FCN.forward (networks.py:16-26).  x: f32 [B,C,96,96] (NCHW) or [B,96,96,C] (NHWC);

@@ -36,7 +36,7 @@ _PROTOS = {
     'simq_set_backend': (C.c_int, [_c_ctx, C.c_int]),
     'simq_set_precision': (C.c_int, [_c_ctx, C.c_int]),
     'simq_set_schedule': (C.c_int, [_c_ctx, C.c_int]),
-    'simq_set_backward_terms': (C.c_int, [_c_ctx, C.c_int, C.c_int]),
+    'simq_set_backward_terms': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_int]),
     'simq_workspace_bytes': (C.c_size_t, [_c_ctx]),
     'simq_fcn_forward': (C.c_int, [_c_ctx, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_uint64, _p]),
     'simq_fcn_backward': (C.c_int, [_c_ctx, _p, _p, C.c_int, _p, C.c_int, _p, _p]),

@@ -136,6 +136,7 @@ struct simq_ctx {
     int device, maxB, backend;
     int terms;                       // 3 = parity mode (default), 1 = bf16 fast mode (simq_set_precision)
     int terms_dgrad, terms_wgrad;    // backward GEMMs: = terms, or 2 (dy contributes its hi plane only; simq_set_backward_terms)
+    int dgrad2_min_planes;           // two-term dgrad only for the residual blocks with at least this many planes
     NetDesc d;
     char* pool; size_t pool_bytes, pool_used;
     ActSet set[3];                   // 0: saved (differentiated forward), 1: scratch (no-grad forwards), 2: eval-only (concurrent target pass)
@@ -285,7 +286,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     SIMQ_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { simq_set_error("simq_ctx_create: device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor); return 2; }
     simq_ctx* c = new simq_ctx();
-    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = c->terms_dgrad = c->terms_wgrad = 3;
+    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = c->terms_dgrad = c->terms_wgrad = 3; c->dgrad2_min_planes = 0;
     build_desc(c->d, C, A);
     c->pool = nullptr;
     carve_all(c, true);
@@ -317,7 +318,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
                 PackEntry& E = host[i];
                 E.start = start; E.w_off = c->d.poff[convs[i].w]; E.cout = convs[i].cout; E.cin = convs[i].cin; E.kk = convs[i].k * convs[i].k; E.bk = convs[i].cout < 64 ? 64 : 0;
                 E.fhi = c->packed[p].fwd[i].hi; E.flo = c->packed[p].fwd[i].lo; E.bhi = c->packed[p].bwd[i].hi; E.blo = c->packed[p].bwd[i].lo;
-                start += (long long)E.cout * E.cin * E.kk;
+                start += (long long)(E.cout / 32) * (E.cin / 32);          // tiles of 32 x 32 (cout x cin); every conv of the net is a multiple
             }
             c->packed[p].n_table = (int)convs.size(); c->packed[p].table_total = start;
             e = cudaMemcpy(c->packed[p].table, host.data(), sizeof(PackEntry) * host.size(), cudaMemcpyHostToDevice);
@@ -360,10 +361,10 @@ extern "C" int simq_set_precision(simq_ctx* c, int mode) {
     ++c->pack_epoch;                 // invalidates captured graphs (the key carries pack_epoch)
     return 0;
 }
-extern "C" int simq_set_backward_terms(simq_ctx* c, int dgrad_terms, int wgrad_terms) {
+extern "C" int simq_set_backward_terms(simq_ctx* c, int dgrad_terms, int wgrad_terms, int dgrad2_min_planes) {
     if (!c || (dgrad_terms != 2 && dgrad_terms != 3) || (wgrad_terms != 2 && wgrad_terms != 3)) { simq_set_error("simq_set_backward_terms: terms must be 2 or 3"); return 1; }
     if (c->terms != 3) { simq_set_error("simq_set_backward_terms: only meaningful in parity mode"); return 1; }
-    c->terms_dgrad = dgrad_terms; c->terms_wgrad = wgrad_terms;
+    c->terms_dgrad = dgrad_terms; c->terms_wgrad = wgrad_terms; c->dgrad2_min_planes = dgrad2_min_planes;
     ++c->pack_epoch;
     return 0;
 }
@@ -685,7 +686,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     TRY(bias_grad(c, c->dy2h, R48, HEAD2_DY_STRIDE, c->sums, M));
     SIMQ_CUDA(cudaMemcpyAsync(grads + d.poff[d.h2_bias], c->sums, sizeof(float) * 32, cudaMemcpyDeviceToDevice, s));
     ConvEpilogue ep0 = conv_ep(0);
-    TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M, c->terms_dgrad));
+    TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M, c->terms));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     float* G = c->G[0];
     float* Gn = c->G[1];
@@ -711,7 +712,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     int g_parts = 0;                 // partial rows already available for the BN consuming G
     {
         ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
-        TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M, c->terms_dgrad));
+        TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M, c->terms));
         g_parts = e.bn_raw ? nparts_fused : 0;
     }
     { float* t = G; G = Gn; Gn = t; }
@@ -721,6 +722,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         auto& Ab = S.blk[b];
         Split in = b == 0 ? S.a0 : S.blk[b - 1].out;
         const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
+        const int dterms = P.planes >= c->dgrad2_min_planes ? c->terms_dgrad : c->terms;     // simq_set_backward_terms
         // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
         cur ^= 1; TRY(acquire(cur));
         if (P.has_ds) TRY(acquire(BUF_B));
@@ -729,7 +731,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         TRY(wgrad_on_w(cur, dyA[cur], Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w]));
         if (P.has_ds) TRY(wgrad_on_w(BUF_B, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w]));
         ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
-        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M, c->terms_dgrad));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M, dterms));
         // b1 = relu(bn1(raw1))
         cur ^= 1; TRY(acquire(cur));
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
@@ -744,7 +746,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
             ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
             g_parts = ep.bn_raw ? nparts_fused : 0;
         }
-        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M, c->terms_dgrad));
+        TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M, dterms));
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
@@ -752,7 +754,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
                 epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
                 g_parts = epd.bn_raw ? nparts_fused : 0;
             }
-            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M, c->terms_dgrad));
+            TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M, dterms));
         }
         { float* t = G; G = Gn; Gn = t; }
     }

@@ -42,7 +42,7 @@ int k_sgd_step(float* params, float* grads, float* momentum, long long n, float 
 // ---- weight packing: OIHW fp32 -> split bf16 [tap][n][k] ----
 // fwd: n = cout, k = cin.   bwd (dgrad): n = cin, k = cout, taps flipped.
 int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split bwd, cudaStream_t s);
-// all convs of a network in ONE launch: table entry = one conv (elements [start, start + cout*cin*kk) of the launch)
+// all convs of a network in ONE launch: table entry = one conv; `start` = its first 32 x 32 (cout x cin) tile, `total` = tiles
 struct PackEntry { long long start; long long w_off; int cout, cin, kk, bk /* dgrad K stride, 0 = cout */; bf16 *fhi, *flo, *bhi, *blo; };
 int k_pack_all(const float* params, const PackEntry* table_dev, int n, long long total, cudaStream_t s);
 

@@ -185,50 +185,69 @@ int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* 
 // ------------------------------------------------------------------------------------------
 // BN apply (+ residual) + ReLU -> split bf16 activation   (resnet.py:35-36, 39-45)
 // ------------------------------------------------------------------------------------------
+// One thread owns 8 consecutive channels for the whole launch (their scale / shift live in registers) and walks down the rows
+// with a grid stride, two rows per trip with all their loads issued before the first use: per element only the streaming
+// operands are loaded (raw 4 B, residual 4 B, out 4 B), and enough bytes are in flight to cover the DRAM latency.
+template <int RES_MODE>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ raw, long long rows, int C,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       int res_mode, Split res, const float* __restrict__ rawd,
+                                                       Split res, const float* __restrict__ rawd,
                                                        const float* __restrict__ scaled, const float* __restrict__ shiftd,
                                                        int pitch25, Split out) {
-    const int C8 = C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * C8) return;
-    long long row = idx / C8;
-    int c = (int)(idx % C8) * 8;
-    size_t off = (size_t)row * C + c;
-    float o[8];
-    if (pitch25 && !p25_valid((int)(row % IMG25))) {
+    const int C8 = C >> 3, rpi = 256 / C8;           // rows per block iteration
+    const int c = (threadIdx.x % C8) * 8, rl = threadIdx.x / C8;
+    float sc[8], sh[8], s2[8], h2[8];
+    load8(scale + c, sc); load8(shift + c, sh);
+    if (RES_MODE == 2) { load8(scaled + c, s2); load8(shiftd + c, h2); }
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += 2 * stride) {
+        const long long rr[2] = {r0, r0 + stride};
+        float v[2][8], r[2][8];
+        bf16x8 rh[2], rlo[2];
+        bool live[2], valid[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        store8_split(out, off, o);
-        return;
+        for (int u = 0; u < 2; ++u) {
+            live[u] = rr[u] < rows;
+            valid[u] = live[u] && !(pitch25 && !p25_valid((int)(rr[u] % IMG25)));
+            const size_t off = (size_t)(live[u] ? rr[u] : r0) * C + c;
+            if (valid[u]) {
+                load8(raw + off, v[u]);
+                if (RES_MODE == 1) { rh[u] = *reinterpret_cast<const bf16x8*>(res.hi + off); rlo[u] = *reinterpret_cast<const bf16x8*>(res.lo + off); }
+                if (RES_MODE == 2) load8(rawd + off, r[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            const size_t off = (size_t)rr[u] * C + c;
+            float o[8];
+            if (!valid[u]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float x = fmaf(v[u][i], sc[i], sh[i]);
+                    if (RES_MODE == 1) x += bf2f(rh[u].v[i]) + bf2f(rlo[u].v[i]);
+                    if (RES_MODE == 2) x += fmaf(r[u][i], s2[i], h2[i]);
+                    o[i] = fmaxf(x, 0.f);
+                }
+            }
+            store8_split(out, off, o);
+        }
     }
-    float v[8], sc[8], sh[8];
-    load8(raw + off, v); load8(scale + c, sc); load8(shift + c, sh);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(v[i], sc[i], sh[i]);
-    if (res_mode == 1) {
-        float r[8];
-        load8_split(res, off, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += r[i];
-    } else if (res_mode == 2) {
-        float r[8], s2[8], h2[8];
-        load8(rawd + off, r); load8(scaled + c, s2); load8(shiftd + c, h2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += fmaf(r[i], s2[i], h2[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-    store8_split(out, off, o);
 }
 
 int k_bn_apply(const float* raw, long long rows, int C, const float* scale, const float* shift, int res_mode,
                Split res, const float* rawd, const float* scaled, const float* shiftd, int pitch25, Split out,
                cudaStream_t s) {
-    long long n = rows * (C / 8);
-    bn_apply_kernel<<<grid_for(n, 256), 256, 0, s>>>(raw, rows, C, scale, shift, res_mode, res, rawd, scaled, shiftd,
-                                                     pitch25, out);
+    if (C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0) { simq_set_error("k_bn_apply: C=%d", C); return 1; }
+    const int rpi = 256 / (C / 8);
+    long long want = (rows + 2 * rpi - 1) / (2 * rpi);          // at least two rows per thread where the problem allows
+    const int grid = (int)(want < 1 ? 1 : want > 8 * 148 ? 8 * 148 : want);
+    if (res_mode == 0) bn_apply_kernel<0><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
+    else if (res_mode == 1) bn_apply_kernel<1><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
+    else bn_apply_kernel<2><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
@@ -564,14 +583,24 @@ __global__ void __launch_bounds__(256) sgd_update_kernel(float* __restrict__ p, 
     }
     __syncthreads();
     const float coef = s_coef;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float gi = g[i] * coef;
-        g[i] = gi;                               // clip_grad_norm_ rescales .grad in place
-        float d = gi + wd * p[i];
-        float b = first_step ? d : mom * m[i] + d;
-        m[i] = b;
-        p[i] = p[i] - lr * b;
+    auto upd = [&](float& pi, float& gi, float& mi) {
+        gi = gi * coef;                          // clip_grad_norm_ rescales .grad in place
+        const float d = gi + wd * pi;
+        const float b = first_step ? d : mom * mi + d;
+        mi = b;
+        pi = pi - lr * b;
+    };
+    const long long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pv = p4[i], gv = g4[i], mv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : m4[i];
+        upd(pv.x, gv.x, mv.x); upd(pv.y, gv.y, mv.y); upd(pv.z, gv.z, mv.z); upd(pv.w, gv.w, mv.w);
+        g4[i] = gv; m4[i] = mv; p4[i] = pv;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n4 << 2; i < n; ++i) upd(p[i], g[i], m[i]);
 }
 
 int k_sgd_step(float* params, float* grads, float* momentum, long long n, float lr, float mom, float wd,
@@ -612,36 +641,48 @@ int k_pack_weights(const float* w, int cout, int cin, int kk, Split fwd, Split b
 }
 
 #define PACK_MAX 32
+#define PACK_T 32                 // tile: 32 output channels x 32 input channels x all taps of one conv
+// All conv weights of a network in ONE launch.  `start` of a table entry counts 32 x 32 tiles.  A block stages its tile of
+// the OIHW tensor in shared memory with coalesced reads (for one co the 32 ci x kk taps are contiguous), then writes the
+// forward shadow [t][co][ci] with ci fastest and the dgrad shadow [kk-1-t][ci][co] with co fastest: both coalesced.  (The
+// element-per-thread version read with a stride of kk floats and ran at 9 % of the copy bandwidth, at the head of every step.)
 __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ params, const PackEntry* __restrict__ table, int n,
                                                        long long total) {
     __shared__ PackEntry tb[PACK_MAX];
+    __shared__ float tile[PACK_T][PACK_T * 9 + 1];
     for (int i = threadIdx.x; i < n; i += blockDim.x) tb[i] = table[i];
     __syncthreads();
-    const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gidx >= total) return;
+    const long long blk = blockIdx.x;
+    if (blk >= total) return;
     int e = 0;
-    while (e + 1 < n && gidx >= tb[e + 1].start) ++e;
+    while (e + 1 < n && blk >= tb[e + 1].start) ++e;
     const PackEntry& E = tb[e];
-    const long long idx = gidx - E.start;
-    const float* w = params + E.w_off;
     const int cin = E.cin, cout = E.cout, kk = E.kk;
-    {   // forward pack: [t][co][ci]
-        int ci = (int)(idx % cin), co = (int)((idx / cin) % cout), t = (int)(idx / ((long long)cin * cout));
-        float v = w[((size_t)co * cin + ci) * kk + t];
-        split_store(v, E.fhi[idx], E.flo[idx]);
+    const int tiles_ci = cin / PACK_T;
+    const int lt = (int)(blk - E.start), co0 = (lt / tiles_ci) * PACK_T, ci0 = (lt % tiles_ci) * PACK_T;
+    const float* w = params + E.w_off;
+    const int row = PACK_T * kk;                                  // contiguous floats of one co within the tile
+    for (int i = threadIdx.x; i < PACK_T * row; i += 256) {
+        const int col = i / row, j = i - col * row;               // j = ci_l * kk + t
+        tile[col][j] = w[((size_t)(co0 + col) * cin + ci0) * kk + j];
     }
-    {   // dgrad pack: [t][ci][co] with the taps rotated by 180 degrees
-        int co = (int)(idx % cout), ci = (int)((idx / cout) % cin), t = (int)(idx / ((long long)cin * cout));
-        float v = w[((size_t)co * cin + ci) * kk + (kk - 1 - t)];
-        // bk > cout: the contraction dim of the dgrad GEMM is zero-padded to bk (the padding is never written: the pool is zero-filled)
-        const size_t o = E.bk > cout ? ((size_t)t * cin + ci) * E.bk + co : (size_t)idx;
-        split_store(v, E.bhi[o], E.blo[o]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < PACK_T * row; i += 256) {
+        const int ci_l = i % PACK_T, co_l = (i / PACK_T) % PACK_T, t = i / (PACK_T * PACK_T);
+        const size_t o = ((size_t)t * cout + co0 + co_l) * cin + ci0 + ci_l;      // forward pack: [t][co][ci]
+        split_store(tile[co_l][ci_l * kk + t], E.fhi[o], E.flo[o]);
+    }
+    const int bk = E.bk > cout ? E.bk : cout;    // bk > cout: the contraction dim of the dgrad GEMM is zero-padded (never written: the pool is zero-filled)
+    for (int i = threadIdx.x; i < PACK_T * row; i += 256) {
+        const int co_l = i % PACK_T, ci_l = (i / PACK_T) % PACK_T, t = i / (PACK_T * PACK_T);
+        const size_t o = ((size_t)(kk - 1 - t) * cin + ci0 + ci_l) * bk + co0 + co_l;  // dgrad pack: [t'][ci][co], taps rotated by 180 degrees
+        split_store(tile[co_l][ci_l * kk + t], E.bhi[o], E.blo[o]);
     }
 }
 
 int k_pack_all(const float* params, const PackEntry* table_dev, int n, long long total, cudaStream_t s) {
     if (n > PACK_MAX) { simq_set_error("k_pack_all: %d entries > %d", n, PACK_MAX); return 1; }
-    pack_all_kernel<<<grid_for(total, 256), 256, 0, s>>>(params, table_dev, n, total);
+    pack_all_kernel<<<(unsigned)total, 256, 0, s>>>(params, table_dev, n, total);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
@@ -921,7 +962,12 @@ int k_bn_bwd_reduce(const float* G, long long rows, int C, int mask_mode, const 
     return 0;
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ G, long long rows, int C, int mask_mode,
+// Same structure as bn_apply_kernel: a thread owns 8 channels (mean / invstd / the three per-channel coefficients of
+//   dy = gamma*invstd * (dz - s1/N - xhat*s2/N)
+// stay in registers), rows are walked with a grid stride, two per trip, every streaming load (G, raw, mask, rawd) issued before
+// the first use.  The arithmetic per element is unchanged (same operations in the same order as the one-row-per-thread version).
+template <int MASK_MODE, bool HAS_DS>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ G, long long rows, int C,
                                                            const bf16* __restrict__ mask_hi, const float* __restrict__ raw,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -930,60 +976,61 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ rawd, const float* __restrict__ meand,
                                                            const float* __restrict__ invstdd, const float* __restrict__ gammad,
                                                            Split dyd, float* dgamma, float* dbeta, float* dgammad, float* dbetad) {
-    const int C8 = C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * C8) return;
-    long long row = idx / C8;
-    int c = (int)(idx % C8) * 8;
-    size_t off = (size_t)row * C + c;
-    float s1[8], s2[8];
+    const int C8 = C >> 3, rpi = 256 / C8;
+    const int c = (threadIdx.x % C8) * 8, rl = threadIdx.x / C8;
+    float s1[8], s2[8], mu[8], is[8], ga[8], sc[8], sh[8], s3[8], mud[8], isd[8], gad[8];
     load8(sums + c, s1); load8(sums + C + c, s2);
-    if (row == 0) {                                   // parameter gradients of the affine BN
+    load8(mean + c, mu); load8(invstd + c, is); load8(gamma + c, ga);
+    if (MASK_MODE == 2) { load8(scale + c, sc); load8(shift + c, sh); }
+    if (HAS_DS) { load8(sums + 2 * C + c, s3); load8(meand + c, mud); load8(invstdd + c, isd); load8(gammad + c, gad); }
+    if (blockIdx.x == 0 && rl == 0) {                 // parameter gradients of the affine BN
         store8(dgamma + c, s2); store8(dbeta + c, s1);
-        if (rawd) { float s3[8]; load8(sums + 2 * C + c, s3); store8(dgammad + c, s3); store8(dbetad + c, s1); }
+        if (HAS_DS) { store8(dgammad + c, s3); store8(dbetad + c, s1); }
     }
-    float o[8], od[8];
-    bool valid = !(pitch25 && !p25_valid((int)(row % IMG25)));
-    if (!valid) {
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += 2 * stride) {
+        const long long rr[2] = {r0, r0 + stride};
+        float g[2][8], rv[2][8], rd[2][8];
+        bf16x8 mh[2];
+        bool live[2], valid[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { o[i] = 0.f; od[i] = 0.f; }
-    } else {
-        float g[8], rv[8], mu[8], is[8], ga[8];
-        load8(G + off, g); load8(raw + off, rv); load8(mean + c, mu); load8(invstd + c, is); load8(gamma + c, ga);
-        bool m[8];
-        if (mask_mode == 1) {
-            bf16x8 mh = *reinterpret_cast<const bf16x8*>(mask_hi + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = bf2f(mh.v[i]) > 0.f;
-        } else if (mask_mode == 2) {
-            float sc[8], sh[8];
-            load8(scale + c, sc); load8(shift + c, sh);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = fmaf(rv[i], sc[i], sh[i]) > 0.f;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = true;
-        }
-        float dz[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dz[i] = m[i] ? g[i] : 0.f;
-            float xh = (rv[i] - mu[i]) * is[i];
-            o[i] = ga[i] * is[i] * (dz[i] - s1[i] * inv_count - xh * s2[i] * inv_count);
-        }
-        if (rawd) {
-            float s3[8], rd[8], mud[8], isd[8], gad[8];
-            load8(sums + 2 * C + c, s3); load8(rawd + off, rd); load8(meand + c, mud); load8(invstdd + c, isd);
-            load8(gammad + c, gad);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float xh = (rd[i] - mud[i]) * isd[i];
-                od[i] = gad[i] * isd[i] * (dz[i] - s1[i] * inv_count - xh * s3[i] * inv_count);
+        for (int u = 0; u < 2; ++u) {
+            live[u] = rr[u] < rows;
+            valid[u] = live[u] && !(pitch25 && !p25_valid((int)(rr[u] % IMG25)));
+            const size_t off = (size_t)(live[u] ? rr[u] : r0) * C + c;
+            if (valid[u]) {
+                load8(G + off, g[u]); load8(raw + off, rv[u]);
+                if (MASK_MODE == 1) mh[u] = *reinterpret_cast<const bf16x8*>(mask_hi + off);
+                if (HAS_DS) load8(rawd + off, rd[u]);
             }
         }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            const size_t off = (size_t)rr[u] * C + c;
+            float o[8], od[8];
+            if (!valid[u]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { o[i] = 0.f; od[i] = 0.f; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    bool m = true;
+                    if (MASK_MODE == 1) m = bf2f(mh[u].v[i]) > 0.f;
+                    if (MASK_MODE == 2) m = fmaf(rv[u][i], sc[i], sh[i]) > 0.f;
+                    const float dz = m ? g[u][i] : 0.f;
+                    const float xh = (rv[u][i] - mu[i]) * is[i];
+                    o[i] = ga[i] * is[i] * (dz - s1[i] * inv_count - xh * s2[i] * inv_count);
+                    if (HAS_DS) {
+                        const float xd = (rd[u][i] - mud[i]) * isd[i];
+                        od[i] = gad[i] * isd[i] * (dz - s1[i] * inv_count - xd * s3[i] * inv_count);
+                    }
+                }
+            }
+            if (dy_f32) store8(dy_f32 + off, o); else store8_split(dy, off, o);
+            if (HAS_DS) store8_split(dyd, off, od);
+        }
     }
-    if (dy_f32) store8(dy_f32 + off, o); else store8_split(dy, off, o);
-    if (rawd) store8_split(dyd, off, od);
 }
 
 int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const bf16* mask_hi, const float* raw,
@@ -991,10 +1038,19 @@ int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const b
                    const float* sums, double count, int pitch25, Split dy, float* dy_f32, const float* rawd,
                    const float* meand, const float* invstdd, const float* gammad, Split dyd, float* dgamma,
                    float* dbeta, float* dgammad, float* dbetad, cudaStream_t s) {
-    long long n = rows * (C / 8);
-    bn_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, s>>>(G, rows, C, mask_mode, mask_hi, raw, scale, shift, mean, invstd,
-                                                         gamma, sums, (float)(1.0 / count), pitch25, dy, dy_f32, rawd,
-                                                         meand, invstdd, gammad, dyd, dgamma, dbeta, dgammad, dbetad);
+    if (C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0) { simq_set_error("k_bn_bwd_apply: C=%d", C); return 1; }
+    const int rpi = 256 / (C / 8);
+    long long want = (rows + 2 * rpi - 1) / (2 * rpi);
+    const int grid = (int)(want < 1 ? 1 : want > 8 * 148 ? 8 * 148 : want);
+    const float inv = (float)(1.0 / count);
+#define BWD_APPLY(MM, DS) bn_bwd_apply_kernel<MM, DS><<<grid, 256, 0, s>>>(G, rows, C, mask_hi, raw, scale, shift, mean, invstd, gamma, sums, inv, \
+        pitch25, dy, dy_f32, rawd, meand, invstdd, gammad, dyd, dgamma, dbeta, dgammad, dbetad)
+    if (rawd) {
+        if (mask_mode == 1) BWD_APPLY(1, true); else if (mask_mode == 2) BWD_APPLY(2, true); else BWD_APPLY(0, true);
+    } else {
+        if (mask_mode == 1) BWD_APPLY(1, false); else if (mask_mode == 2) BWD_APPLY(2, false); else BWD_APPLY(0, false);
+    }
+#undef BWD_APPLY
     SIMQ_LAUNCH_CHECK();
     return 0;
 }

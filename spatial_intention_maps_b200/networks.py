@@ -237,10 +237,11 @@ class FCN(nn.Module):
         self._precision = m
         _lib.check(_lib.lib().simq_set_precision(self.ctx().handle, m), 'simq_set_precision')
 
-    def set_backward_terms(self, dgrad: int = 3, wgrad: int = 3):
-        """Operand terms of the backward GEMMs (3 = default split-bf16 scheme; 2 = the output gradient contributes its bf16 hi
-        plane only: 2 MMAs per product).  The forward passes -- Q-map and arg-max parity -- are unaffected."""
-        self._bwd_terms = (int(dgrad), int(wgrad))
+    def set_backward_terms(self, dgrad: int = 3, wgrad: int = 3, dgrad2_min_planes: int = 0):
+        """Operand terms of the backward GEMMs (3 = the forward's split-bf16 scheme; 2 = the output gradient contributes its bf16
+        hi plane only: 2 MMAs per product).  ``dgrad`` applies to the residual blocks with at least ``dgrad2_min_planes`` planes.
+        The forward passes -- Q-map and arg-max parity -- are unaffected."""
+        self._bwd_terms = (int(dgrad), int(wgrad), int(dgrad2_min_planes))
         _lib.check(_lib.lib().simq_set_backward_terms(self.ctx().handle, *self._bwd_terms), 'simq_set_backward_terms')
 
     def set_schedule(self, mode: str):
