@@ -438,8 +438,9 @@ def run_simq(args):
     # and the serial schedule, so this pass is separate from the one that defines `value`)
     L.simq_profile(1, None, None, None)
     ms_prof = timed(step_device, args.steps)
-    pm, pf, pl = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+    pm, pf, pl, pi = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)(), (C.c_double * 2)()
     L.simq_profile(0, pm, pf, pl)
+    L.simq_profile_issued(pi)
     # ---- the literal user call train.train(cfg, ..., batch of numpy arrays, ...) incl. host staging ----
     cfg = types.SimpleNamespace(batch_size=B, grad_norm_clipping=100, use_double_dqn=True)
 
@@ -473,6 +474,20 @@ def run_simq(args):
         del buf, samples
     except Exception as e:  # noqa: BLE001
         replay = {'error': f'{type(e).__name__}: {e}'}
+    # ---- the same step with three operand terms in EVERY backward GEMM (simq_set_backward_terms(3, 3, 0)) ----
+    full3 = None
+    if not args.no_serial:
+        pol.set_backward_terms(3, 3, 0)
+        for i in range(warm):
+            step_device(i)
+        ms_full3 = timed(step_device, args.steps)
+        pol.set_backward_terms(2, 2, 512)
+        for i in range(warm):
+            step_device(i)
+        full3 = {'ms_per_step': ms_full3 / args.steps, 'value': world * B * args.steps / (ms_full3 * 1e-3), 'unit': UNIT,
+                 'note': 'simq_set_backward_terms(3, 3, 0): dy keeps both bf16 planes in every weight-gradient / input-gradient GEMM (3 MMAs per '
+                         'product); the default uses dy.hi only in the weight-gradient GEMMs and the layer-4 input-gradient convolutions '
+                         '(gradient error vs the float64 twin +6 %, profiles/r2_bwd_terms_probe.md); forward passes identical'}
     # ---- the same step under the serial schedule (one stream; simq_set_schedule) ----
     serial = None
     if not args.no_serial:
@@ -593,7 +608,8 @@ def run_simq(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
             'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None,
-            'dtype': 'bf16 hi+lo split operands (3 tcgen05 MMAs per product), f32 accumulate',
+            'dtype': 'bf16 hi+lo split operands, f32 accumulate: 3 tcgen05 MMAs per product in every forward pass (Q-map / arg-max parity); '
+                     'backward: 2 MMAs (dy.hi x split operand) in the weight-gradient GEMMs and the layer-4 input-gradient convolutions, 3 elsewhere',
             'data': 'synthetic (U[0,1) states)' if args.uniform_input else 'synthetic',
             'config': {'workload': workload_name(B), 'global_batch': world * B, 'parallelism': f'dp{world}',
                        'batches_rotated': N_BATCHES,
@@ -613,18 +629,20 @@ def run_simq(args):
                          'share_of_step': (pm[0] / args.steps) / (ms_prof / args.steps), 'ms_per_step_profiled_pass': ms_prof / args.steps,
                          'profiled_pass': 'eager launches, serial schedule (one stream), CUDA events around every tensor-core launch: a '
                                           'kernel\'s events time that kernel alone; `value` comes from the graphed multi-lane pass',
-                         'note': 'algorithmic FLOPs (2*valid_pixels*N*K*taps); the kernel issues 3 bf16 MMAs per product over 625/576 padded rows, '
-                                 'so issued tensor work = 3.26x algorithmic: issued_frac = frac*3.26',
-                         'issued_frac': conv_tf * 3 * 625 / 576 / sustained,
-                         'parity_mode_ceiling_frac': 576.0 / (3 * 625), 'frac_of_parity_mode_ceiling': conv_tf * 3 * 625 / 576 / sustained,
+                         'note': 'achieved = ALGORITHMIC FLOPs (2*valid_pixels*N*K*taps) / time; the kernels issue 3 (forward, most dgrads) or 2 '
+                                 '(layer-4 dgrads) bf16 MMAs per product over 625/576 padded rows: issued_frac counts those',
+                         'issued_tflops': (pi[0] / (pm[0] * 1e-3)) / 1e12 if pm[0] > 0 else 0.0,
+                         'issued_frac': (pi[0] / (pm[0] * 1e-3)) / 1e12 / sustained if pm[0] > 0 else 0.0,
+                         'algorithmic_ceiling_frac': pf[0] / pi[0] if pi[0] > 0 else None,
                          'wgrad_kernel': {'achieved': wgrad_tf, 'frac': wgrad_tf / sustained, 'launches': int(pl[1]),
-                                          'ms_per_step_in_kernel': pm[1] / args.steps},
+                                          'ms_per_step_in_kernel': pm[1] / args.steps,
+                                          'issued_frac': (pi[1] / (pm[1] * 1e-3)) / 1e12 / sustained if pm[1] > 0 else 0.0},
                          'step_tflops_algorithmic': STEP_GFLOP * 1e-3 * value,
                          'step_frac_of_peak': STEP_GFLOP * 1e-3 * value / world / sustained,
                          'fwd_bwd_only': {'value': world * B / (ms_fb * 1e-3), 'unit': UNIT, 'ms': ms_fb,
                                           'note': 'the literal BASELINE.json metric: online forward on s + backward through the autograd.Function route'},
                          'forward_only': {'value': world * B / (ms_f * 1e-3), 'unit': UNIT, 'ms': ms_f, 'note': 'train-mode BN, no_grad'},
-                         'serial_schedule': serial},
+                         'serial_schedule': serial, 'three_term_backward': full3},
             'clocks': clocks, 'loss': loss,
         }
         if world == 1:

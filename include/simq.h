@@ -38,7 +38,7 @@ typedef void* simq_stream;            /* cudaStream_t */
  * fp32 comparator for tests/debug (never the default). */
 enum { SIMQ_BACKEND_UMMA = 0, SIMQ_BACKEND_FMA = 1 };
 /* tensor-core operand precision.  PARITY (default): every operand is a bf16 hi+lo pair and every product
- * three MMAs (meets the 1e-3 Q-map / arg-max bar).  BF16: hi planes only, one MMA per product -- ~2.5x faster
+ * three MMAs in every FORWARD pass (meets the 1e-3 Q-map / arg-max bar; backward GEMMs: see simq_set_backward_terms).  BF16: hi planes only, one MMA per product -- ~2.5x faster
  * conv kernels, Q-map error ~1e-2 (FAILS the parity bar; opt-in for users who train in bf16 anyway). */
 enum { SIMQ_PRECISION_PARITY = 0, SIMQ_PRECISION_BF16 = 1 };
 /* how the independent pieces of a step are scheduled.  LANES (default): two streams forked / joined with events -- the
@@ -65,12 +65,15 @@ void simq_ctx_destroy(simq_ctx*);
 int simq_set_backend(simq_ctx*, int backend);
 int simq_set_precision(simq_ctx*, int mode);
 int simq_set_schedule(simq_ctx*, int mode);
-/* Operand terms of the BACKWARD GEMMs in parity mode (default 3, 3 = the forward's split-bf16 scheme).  2: the output
+/* Operand terms of the BACKWARD GEMMs in parity mode.  3 = the forward's split-bf16 scheme.  2: the output
  * gradient dy contributes only its bf16 hi plane (hi*lo + hi*hi: two MMAs per product and no dy.lo loads) -- dgrad_terms for
  * the input-gradient convolutions of the residual blocks with at least dgrad2_min_planes planes (their rounding propagates down
  * the chain; the head's 1x1 convs always keep 3), wgrad_terms for the weight-gradient GEMMs (80 000-term sums: the rounding
  * averages out).  The forward passes -- everything the Q-map / arg-max parity bar covers -- are
- * never affected.  Opt-in; see DESIGN.md for the measured gradient error against the float64 twin. */
+ * never affected.  DEFAULT: (2, 2, 512) -- weight gradients and the layer-4 input gradients with two terms: measured against the
+ * float64 twin of the reference the gradient error grows by <= 6 % (1.18e-2 -> 1.25e-2 flat rel-L2; the fp32 reference itself sits at
+ * 0.4e-2) for -10 % step time; (3, 3, 0) restores three terms everywhere (env SIMQ_BWD_TERMS=3 makes that the default).  DESIGN.md
+ * section 3 has the table. */
 int simq_set_backward_terms(simq_ctx*, int dgrad_terms, int wgrad_terms, int dgrad2_min_planes);
 size_t simq_workspace_bytes(const simq_ctx*);
 
@@ -158,6 +161,9 @@ int64_t simq_launch_count(const simq_ctx*);
  * kernel incl. its split reduction; any may be NULL to discard), then enables or disables recording
  * (CUDA events around every launch of those classes, on the launching stream). */
 int simq_profile(int enable, double* ms, double* flops, long long* launches);
+/* Tensor-core FLOPs actually ISSUED by the launches the last simq_profile call collected (operand terms x all rows incl. the
+ * pitch-25 halo rows), per class: array of 2. */
+int simq_profile_issued(double* issued);
 
 /* ---- test hooks (exercise single kernels through the C-ABI; used by tests/ only) ---- */
 /* Copy an internal activation of the last forward (set 0 = saved set, 1 = scratch set) as dense

@@ -54,6 +54,7 @@ _PROTOS = {
     'simq_greedy_action': (C.c_int, [_c_ctx, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_uint64, _p]),
     'simq_launch_count': (C.c_int64, [_c_ctx]),
     'simq_profile': (C.c_int, [C.c_int, _p, _p, _p]),
+    'simq_profile_issued': (C.c_int, [_p]),
     'simq_debug_get': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
     'simq_debug_tensor_name': (C.c_char_p, [C.c_int]),
     'simq_test_conv': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p]),

@@ -25,32 +25,38 @@ extern "C" int simq_version(void) { return 1; }
 // ------------------------------------------------------------------------------------------------
 // per-kernel-class timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------
-struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, issued; };
 // (thread-local: simq_profile has no context argument; a profile belongs to the thread that enabled it)
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec> g_prof;
 static thread_local std::vector<cudaEvent_t> g_prof_pool;
 void prof_enable(bool on) { g_prof_on = on; }
-void prof_mark(int cls, bool begin, double flops, cudaStream_t s) {
+void prof_mark(int cls, bool begin, double flops, cudaStream_t s, double issued) {
     if (!g_prof_on) return;
     cudaEvent_t e;
     if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
     else if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, s);
-    if (begin) { ProfRec r; r.e0 = e; r.e1 = nullptr; r.cls = cls; r.flops = flops; g_prof.push_back(r); }
+    if (begin) { ProfRec r; r.e0 = e; r.e1 = nullptr; r.cls = cls; r.flops = flops; r.issued = issued; g_prof.push_back(r); }
     else if (!g_prof.empty()) g_prof.back().e1 = e;
 }
+static thread_local double g_prof_issued[PROF_CLASSES] = {0, 0};
 int prof_collect(double* ms, double* flops, long long* launches) {
-    for (int i = 0; i < PROF_CLASSES; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+    for (int i = 0; i < PROF_CLASSES; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; g_prof_issued[i] = 0; }
     for (auto& r : g_prof) {
         if (!r.e1) { g_prof_pool.push_back(r.e0); continue; }
         float t = 0;
         SIMQ_CUDA(cudaEventSynchronize(r.e1));
         SIMQ_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
-        ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1;
+        ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1; g_prof_issued[r.cls] += r.issued;
         g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
     }
     g_prof.clear();
+    return 0;
+}
+extern "C" int simq_profile_issued(double* issued) {      // of the classes collected by the last simq_profile call
+    if (!issued) return 1;
+    for (int i = 0; i < PROF_CLASSES; ++i) issued[i] = g_prof_issued[i];
     return 0;
 }
 extern "C" int simq_profile(int enable, double* ms, double* flops, long long* launches) {
@@ -173,6 +179,10 @@ struct LaunchScope {
     ~LaunchScope() { if (c) c->launch_total += g_simq_launches - l0; }
 };
 
+// Default backward operand scheme of parity mode (accepted against the float64 twin): weight-gradient GEMMs
+// and the layer-4 input-gradient convolutions use dy's hi plane only (2 MMAs per product).  SIMQ_BWD_TERMS=3 restores 3 everywhere.
+static void default_backward_terms(simq_ctx* c);
+
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 template <typename T>
@@ -286,7 +296,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
     SIMQ_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { simq_set_error("simq_ctx_create: device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor); return 2; }
     simq_ctx* c = new simq_ctx();
-    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = c->terms_dgrad = c->terms_wgrad = 3; c->dgrad2_min_planes = 0;
+    c->device = device; c->maxB = max_batch; c->backend = SIMQ_BACKEND_UMMA; c->terms = 3; default_backward_terms(c);
     build_desc(c->d, C, A);
     c->pool = nullptr;
     carve_all(c, true);
@@ -358,8 +368,15 @@ extern "C" int simq_set_backend(simq_ctx* c, int backend) {
 extern "C" int simq_set_precision(simq_ctx* c, int mode) {
     if (!c || (mode != SIMQ_PRECISION_PARITY && mode != SIMQ_PRECISION_BF16)) { simq_set_error("simq_set_precision: bad argument"); return 1; }
     c->terms = c->terms_dgrad = c->terms_wgrad = mode == SIMQ_PRECISION_BF16 ? 1 : 3;
+    if (mode == SIMQ_PRECISION_PARITY) default_backward_terms(c);
     ++c->pack_epoch;                 // invalidates captured graphs (the key carries pack_epoch)
     return 0;
+}
+static void default_backward_terms(simq_ctx* c) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("SIMQ_BWD_TERMS"); forced = e ? atoi(e) : 0; }
+    const int t = forced == 3 ? 3 : 2;
+    c->terms_dgrad = t; c->terms_wgrad = t; c->dgrad2_min_planes = 512;
 }
 extern "C" int simq_set_backward_terms(simq_ctx* c, int dgrad_terms, int wgrad_terms, int dgrad2_min_planes) {
     if (!c || (dgrad_terms != 2 && dgrad_terms != 3) || (wgrad_terms != 2 && wgrad_terms != 3)) { simq_set_error("simq_set_backward_terms: terms must be 2 or 3"); return 1; }
@@ -502,7 +519,7 @@ static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Spli
                    const Lane& L) {
     ConvEpilogue ep = conv_ep(pitch25);
     int nparts = 0;
-    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = L.partials; nparts = umma_conv_m_tiles(rows); }
+    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = L.partials; ep.stat_rows_out = &nparts; }
     TRY(conv_any(c, c->backend, in, rows, K, W, N, ntaps, raw, ep, L));
     return bn_prepare(c, S, b, raw, rows, count, params, bn, nbt, bias_param, training, nparts, L);
 }
@@ -609,7 +626,7 @@ extern "C" int simq_fcn_forward(simq_ctx* c, const float* params, float* bn, int
 // nparts > 0: the dgrad epilogue that produced G already left `nparts` rows of (sum dz, sum dz*xhat) in L.partials
 static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, long long rows, double count, int mask_mode,
                        const bf16* mask_hi, const float* raw, const float* params, float* grads, int pitch25, Split dy,
-                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, const Lane& L) {
+                       float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, const Lane& L, int hi_only = 0) {
     const NetDesc& d = c->d;
     cudaStream_t s = L.s;
     if (nparts > 0) {
@@ -624,7 +641,7 @@ static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, lon
                        bnstat(S, b.idx, BS_MEAN), bnstat(S, b.idx, BS_INVSTD), params + d.poff[b.gamma], c->sums, count, pitch25, dy,
                        dy_f32, rawd, bd ? bnstat(S, bd->idx, BS_MEAN) : nullptr, bd ? bnstat(S, bd->idx, BS_INVSTD) : nullptr,
                        bd ? params + d.poff[bd->gamma] : nullptr, dyd, grads + d.poff[b.gamma], grads + d.poff[b.gamma + 1],
-                       bd ? grads + d.poff[bd->gamma] : nullptr, bd ? grads + d.poff[bd->gamma + 1] : nullptr, s));
+                       bd ? grads + d.poff[bd->gamma] : nullptr, bd ? grads + d.poff[bd->gamma + 1] : nullptr, hi_only, s));
     return 0;
 }
 
@@ -700,11 +717,11 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
     // with a downsample branch need a third sum and keep the separate reduction.
     const bool fuse = be == SIMQ_BACKEND_UMMA;
-    const int nparts_fused = umma_conv_m_tiles(R25);
+    int nparts_fused = 0;            // partial rows the last BN-sum-fusing dgrad launch wrote (ConvEpilogue::stat_rows_out)
     // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
     auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
         if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
-            e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask;
+            e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask; e.stat_rows_out = &nparts_fused;
             e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
         }
         return e;
@@ -723,11 +740,13 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         Split in = b == 0 ? S.a0 : S.blk[b - 1].out;
         const int s1 = conv_slot(d, P.c1.w), s2 = conv_slot(d, P.c2.w);
         const int dterms = P.planes >= c->dgrad2_min_planes ? c->terms_dgrad : c->terms;     // simq_set_backward_terms
+        // every consumer of this block's dy tensors (two dgrads, two or three wgrads) reads the hi plane only: skip the lo planes
+        const int hi_only = (be == SIMQ_BACKEND_UMMA && dterms == 2 && c->terms_wgrad == 2) ? 1 : 0;
         // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
         cur ^= 1; TRY(acquire(cur));
         if (P.has_ds) TRY(acquire(BUF_B));
         TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, dyA[cur], nullptr, P.has_ds ? &P.bds : nullptr,
-                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, M));
+                        P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, M, hi_only));
         TRY(wgrad_on_w(cur, dyA[cur], Ab.b1, R25, P.planes, P.planes, 9, grads + d.poff[P.c2.w]));
         if (P.has_ds) TRY(wgrad_on_w(BUF_B, c->dyB, in, R25, P.planes, P.cin, 1, grads + d.poff[P.ds.w]));
         ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
@@ -735,26 +754,22 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         // b1 = relu(bn1(raw1))
         cur ^= 1; TRY(acquire(cur));
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
-                        none, em.bn_raw ? nparts_fused : 0, M));
+                        none, em.bn_raw ? nparts_fused : 0, M, hi_only));
         TRY(wgrad_on_w(cur, dyA[cur], in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w]));
         // gradient w.r.t. the block input = the previous block's output (or the stem's pooled output for b == 0)
         const bool consumer_fusable = b > 0 && !d.blk[b - 1].has_ds;
         ConvEpilogue ep = ep25;
         if (!P.has_ds) { ep.add_g = G; ep.add_g_mask = Ab.out.hi; }
         g_parts = 0;
-        if (consumer_fusable && !P.has_ds) {
-            ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
-            g_parts = ep.bn_raw ? nparts_fused : 0;
-        }
+        if (consumer_fusable && !P.has_ds) ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
         TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M, dterms));
+        if (ep.bn_raw) g_parts = nparts_fused;            // (the launch has just reported its partial-row count)
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
-            if (consumer_fusable) {
-                epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
-                g_parts = epd.bn_raw ? nparts_fused : 0;
-            }
+            if (consumer_fusable) epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
             TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M, dterms));
+            if (epd.bn_raw) g_parts = nparts_fused;
         }
         { float* t = G; G = Gn; Gn = t; }
     }

@@ -62,6 +62,13 @@ __device__ __forceinline__ void store8_split(const Split& s, size_t off, const f
     *reinterpret_cast<bf16x8*>(s.lo + off) = l;
 }
 
+__device__ __forceinline__ void store8_hi(const Split& s, size_t off, const float* o) {      // hi plane only (two-term consumers)
+    bf16x8 h;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h.v[i] = __float2bfloat16_rn(o[i]);
+    *reinterpret_cast<bf16x8*>(s.hi + off) = h;
+}
+
 // bilinear x2, align_corners=True source index exactly as ATen's area_pixel_compute_source_index +
 // upsample_bilinear2d (fp32): src = dst * (in-1)/(out-1); i0 = (int)src; i1 = i0 + (i0 < in-1);
 // w1 = src - i0; w0 = 1 - w1.    (networks.py:21,25)

@@ -149,7 +149,7 @@ struct ConvCfg {
     static constexpr int W_OFF = A_PLANES * A_BYTES;          // stage layout: A hi [, A lo], W hi [, W lo]
     static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + W_PLANES * W_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4; // per epilogue warp: 32 rows x 32 columns fp32
-    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares
+    static constexpr int CSUM_BYTES = 5 * 2 * BN * 4;         // per epilogue warp column sums / sums of squares + the CTA's running total
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
@@ -168,9 +168,14 @@ enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU 
 // tcgen05.ld 32 columns -> smem staging -> [column sums] -> transforms -> coalesced row stores.
 // CLUSTER: the accumulator-free barrier lives in CTA 0 of the pair (remote arrive).
 // ------------------------------------------------------------------------------------------------
+// Column statistics (EF_STATS / EF_BNBWD): stat_per_cta != 0 -> the tile's sums are added to the CTA's running total (csum + 8*BN,
+// fixed tile order = deterministic) and written ONCE per CTA by flush_cta_stats: the finalize / reduce kernel that follows reads
+// <= 148 partial rows instead of one per m-tile (625 at batch 128); 0 -> one partial row per m-tile (CTAs whose tiles span several
+// column blocks).
 template <int BN, int FL, bool CLUSTER>
 __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint32_t tmem_acc, uint32_t tempty, int m_t, int n0,
-                                              int rows, int N, float* __restrict__ out, const ConvEpilogue& ep, int quad, int lane) {
+                                              int rows, int N, float* __restrict__ out, const ConvEpilogue& ep, int quad, int lane,
+                                              int stat_per_cta) {
     float* stg = staging + quad * 32 * EPI_LD;
     float* cs = csum + quad * 2 * BN;
     const int sr = lane >> 3, scol = (lane & 7) * 4;  // store phase: 4 rows per instruction, float4 per lane
@@ -294,10 +299,25 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
         const int t = threadIdx.x - 64;         // 0..127
         for (int j = t; j < 2 * BN; j += 128) {
             float tot = csum[j] + csum[2 * BN + j] + csum[4 * BN + j] + csum[6 * BN + j];
-            const int which = j / BN, col = j - which * BN;
-            ep.stats[((size_t)m_t * 2 + which) * N + n0 + col] = tot;
+            if (stat_per_cta) {
+                csum[8 * BN + j] += tot;            // always thread t for column j: no race
+            } else {
+                const int which = j / BN, col = j - which * BN;
+                ep.stats[((size_t)m_t * 2 + which) * N + n0 + col] = tot;
+            }
         }
         epi_bar_sync();
+    }
+}
+template <int BN>
+__device__ __forceinline__ void zero_cta_stats(float* csum) {
+    for (int j = threadIdx.x - 64; j < 2 * BN; j += 128) csum[8 * BN + j] = 0.f;
+}
+template <int BN>
+__device__ __forceinline__ void flush_cta_stats(const float* csum, float* __restrict__ stats, int row, int n0, int N) {
+    for (int j = threadIdx.x - 64; j < 2 * BN; j += 128) {
+        const int which = j / BN, col = j - which * BN;
+        stats[((size_t)row * 2 + which) * N + n0 + col] = csum[8 * BN + j];
     }
 }
 
@@ -405,15 +425,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     } else {
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
         int acc = 0; uint32_t aph = 0;
+        constexpr bool HAS_STATS = (FL & (EF_STATS | EF_BNBWD)) != 0;
+        const int stat_per_cta = HAS_STATS && nz == 1 && gridDim.x % n_tiles == 0;      // this CTA's tiles share one column block
+        if (stat_per_cta) zero_cta_stats<BN>(csum);
         for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
             const int tile = work / nz, z = work - tile * nz;
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N,
-                                         out + (size_t)z * rows * N, ep, quad, lane);
+                                         out + (size_t)z * rows * N, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
+        if (stat_per_cta && (int)blockIdx.x < total_tiles)
+            flush_cta_stats<BN>(csum, ep.stats, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N);
     }
     tc_fence_before();
     __syncthreads();
@@ -471,7 +496,7 @@ struct Conv2Cfg {
     static constexpr int W_OFF = A_PLANES * A_BYTES;
     static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + W_PLANES * W_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
-    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
+    static constexpr int CSUM_BYTES = 5 * 2 * BN * 4;
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
     static constexpr int STAGES = TERMS == 3 ? 3 : TERMS == 2 ? 4 : 6;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
@@ -583,14 +608,19 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     } else {
         const int quad = warp & 3;
         int acc = 0; uint32_t aph = 0;
+        constexpr bool HAS_STATS = (FL & (EF_STATS | EF_BNBWD)) != 0;
+        const int stat_per_cta = HAS_STATS && num_clusters % n_tiles == 0;              // this pair's tiles share one column block
+        if (stat_per_cta) zero_cta_stats<BN>(csum);
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
             const int m2 = tile / n_tiles, n0 = (tile - m2 * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             epilogue_tile<BN, FL, true>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m2 * 2 + (int)rank, n0, rows, N,
-                                        out, ep, quad, lane);
+                                        out, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
+        if (stat_per_cta && cluster_id < total_tiles)
+            flush_cta_stats<BN>(csum, ep.stats, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N);
     }
     tc_fence_before();
     cluster_sync_all();             // nobody leaves while the peer may still touch its barriers / TMEM
@@ -632,7 +662,7 @@ struct Conv2WCfg {
     static constexpr int W_BASE = A_BUFS * A_BUF_BYTES;
     static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
-    static constexpr int CSUM_BYTES = 4 * 2 * BN * 4;
+    static constexpr int CSUM_BYTES = 5 * 2 * BN * 4;
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
     static constexpr int SMEM_BYTES = RING_BYTES + FIXED;
     static constexpr int TMEM_COLS = 512;
@@ -771,14 +801,19 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     } else {
         const int quad = warp & 3;
         int acc = 0; uint32_t aph = 0;
+        constexpr bool HAS_STATS = (FL & (EF_STATS | EF_BNBWD)) != 0;
+        const int stat_per_cta = HAS_STATS && num_clusters % n_tiles == 0;              // this pair's tiles share one column block
+        if (stat_per_cta) zero_cta_stats<BN>(csum);
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
             const int m2 = tile / n_tiles, n0 = (tile - m2 * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             epilogue_tile<BN, FL, true>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m2 * 2 + (int)rank, n0, rows, N,
-                                        out, ep, quad, lane);
+                                        out, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
+        if (stat_per_cta && cluster_id < total_tiles)
+            flush_cta_stats<BN>(csum, ep.stats, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N);
     }
     tc_fence_before();
     cluster_sync_all();
@@ -1162,9 +1197,10 @@ static int launch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntap
         return 1;
     const int m_tiles = ceil_div(A.rows, UM_BM), n_tiles = N / BN;
     const int grid = m_tiles * n_tiles * nz < g_num_sms ? m_tiles * n_tiles * nz : g_num_sms;
+    if (ep.stat_rows_out) *ep.stat_rows_out = (nz == 1 && grid % n_tiles == 0) ? grid / n_tiles : m_tiles;     // see epilogue_tile
     // algorithmic FLOPs: 2 * valid output positions * N * K * taps (pitch-25 rows carry 576 of 625 valid)
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
-    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s, 2.0 * TERMS * (double)A.rows * N * A.cols * ntaps);
     conv_umma_kernel<BN, FL, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m_tiles, n_tiles, nz, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
@@ -1184,8 +1220,9 @@ static int launch_conv2(const UmmaTensor& A, const UmmaTensor& W, int N, int nta
     const int m2_tiles = ceil_div(A.rows, 256), n_tiles = N / Cfg::BN;
     int clusters = g_num_sms / 2;
     if (m2_tiles * n_tiles < clusters) clusters = m2_tiles * n_tiles;
+    if (ep.stat_rows_out) *ep.stat_rows_out = clusters % n_tiles == 0 ? 2 * (clusters / n_tiles) : 2 * m2_tiles;    // see epilogue_tile
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
-    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s);
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * ntaps, s, 2.0 * TERMS * (double)A.rows * N * A.cols * ntaps);
     conv2_umma_kernel<FL, TERMS><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, ntaps, m2_tiles,
                                                                         n_tiles, out, ep);
     prof_mark(PROF_CONV, false, 0, s);
@@ -1212,8 +1249,9 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
     const int m2_tiles = ceil_div(A.rows, 256), n_tiles = N / Cfg::BN;
     int clusters = g_num_sms / 2;
     if (m2_tiles * n_tiles < clusters) clusters = m2_tiles * n_tiles;
+    if (ep.stat_rows_out) *ep.stat_rows_out = clusters % n_tiles == 0 ? 2 * (clusters / n_tiles) : 2 * m2_tiles;    // see epilogue_tile
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
-    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * 9, s);
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * 9, s, 2.0 * TERMS * (double)A.rows * N * A.cols * 9);
     conv2w_umma_kernel<FL, TERMS><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, m2_tiles, n_tiles,
                                                                          out, ep);
     prof_mark(PROF_CONV, false, 0, s);
@@ -1353,7 +1391,7 @@ static int launch_wgrad(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, fl
     if (per_split * nsplit > umma_wgrad_scratch_floats()) { simq_set_error("wgrad scratch too small"); return 1; }
     long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(ceil_div(Cout, UM_BM), Cin / BN, ntaps * nsplit);
-    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s);
+    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s, 2.0 * TERMS * (double)rows * Cout * Cin * ntaps);
     wgrad_umma_kernel<BN, TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk,
                                                                   scratch);
     SIMQ_LAUNCH_CHECK();
@@ -1393,7 +1431,7 @@ static int launch_wgrad2(const UmmaTensor& dY, const UmmaTensor& X, int ntaps, f
     if (per_split * nsplit > umma_wgrad_scratch_floats()) { simq_set_error("wgrad scratch too small"); return 1; }
     long long chunk = ((rows + nsplit - 1) / nsplit + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(2 * (Cout / 256), Cin / 256, ntaps * nsplit);
-    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s);
+    prof_mark(PROF_WGRAD, true, 2.0 * (double)rows * 576.0 / 625.0 * Cout * Cin * ntaps, s, 2.0 * TERMS * (double)rows * Cout * Cin * ntaps);
     wgrad2_umma_kernel<TERMS><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mYhi, mYlo, mXhi, mXlo, rows, Cout, Cin, ntaps, nsplit, chunk, scratch);
     SIMQ_LAUNCH_CHECK();
     wgrad_reduce_kernel<<<ceil_div((long long)per_split, 256), 256, 0, s>>>(scratch, Cout, Cin, ntaps, nsplit, dW);

@@ -67,7 +67,8 @@ int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const b
                    const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
                    const float* sums, double count, int pitch25, Split dy, float* dy_f32, const float* rawd,
                    const float* meand, const float* invstdd, const float* gammad, Split dyd, float* dgamma,
-                   float* dbeta, float* dgammad, float* dbetad, cudaStream_t s);
+                   float* dbeta, float* dgammad, float* dbetad, int hi_only /* every consumer of dy is a two-term GEMM: skip the lo planes */,
+                   cudaStream_t s);
 int k_pool_bwd(const float* g_a0, const float* raw0, int B, const float* scale, const float* shift, float* dz0,
                cudaStream_t s);
 int k_colsum_split(Split dy, long long rows, int C, float* partials, cudaStream_t s);   // bias grads: [STAT_BLOCKS][C]
@@ -91,7 +92,8 @@ struct ConvEpilogue {
     Split res;                // v += res.hi + res.lo        (identity shortcut)
     int relu;
     Split out_split;          // write v as split bf16 (out may then be NULL)
-    float* stats;             // [m_tiles][2][N] per-tile column sums / sums of squares of the raw accumulators
+    float* stats;             // [stat rows][2][N] partial column sums / sums of squares of the raw accumulators
+    int* stat_rows_out;       // (host) receives the number of partial rows the launch writes: one per CTA (<= 148) or one per m-tile
     // BatchNorm-backward statistics of the gradient this launch produces (dgrad): with dz = out * [bn_mask > 0],
     // stats rows become (sum dz, sum dz * (bn_raw - mean) * invstd) -- saves the separate reduction pass
     const float* bn_raw; const bf16* bn_mask; const float* bn_mean; const float* bn_invstd;
@@ -104,7 +106,7 @@ static inline ConvEpilogue conv_ep(int pitch25) {
     e.pitch25 = pitch25; e.add_prev = nullptr; e.add_g = nullptr; e.add_g_mask = nullptr; e.scale = nullptr; e.shift = nullptr;
     e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
     e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr; e.terms = 3;
-    e.splitk_scratch = nullptr; e.splitk_floats = 0;
+    e.splitk_scratch = nullptr; e.splitk_floats = 0; e.stat_rows_out = nullptr;
     return e;
 }
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)
@@ -137,5 +139,5 @@ size_t umma_wgrad_scratch_floats();
 // ---- per-kernel-class device timing (bench.py's roofline): CUDA events around the launches of a class ----
 enum { PROF_CONV = 0, PROF_WGRAD = 1, PROF_CLASSES = 2 };
 void prof_enable(bool on);
-void prof_mark(int cls, bool begin, double flops, cudaStream_t s);
+void prof_mark(int cls, bool begin, double flops, cudaStream_t s, double issued = 0);   // issued: tensor-core FLOPs actually issued (terms x all rows)
 int prof_collect(double* ms, double* flops, long long* launches);      // syncs the recorded events; arrays [PROF_CLASSES]

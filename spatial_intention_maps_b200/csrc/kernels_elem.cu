@@ -185,66 +185,54 @@ int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* 
 // ------------------------------------------------------------------------------------------
 // BN apply (+ residual) + ReLU -> split bf16 activation   (resnet.py:35-36, 39-45)
 // ------------------------------------------------------------------------------------------
-// One thread owns 8 consecutive channels for the whole launch (their scale / shift live in registers) and walks down the rows
-// with a grid stride, two rows per trip with all their loads issued before the first use: per element only the streaming
-// operands are loaded (raw 4 B, residual 4 B, out 4 B), and enough bytes are in flight to cover the DRAM latency.
+// One thread = 8 consecutive channels of one row, blocks sweep the tensor linearly.  (A persistent variant -- a thread keeps its
+// channels' scale / shift in registers and walks down the rows with a grid stride -- was measured SLOWER here: 0.65 vs 0.74 of the
+// copy bandwidth over the 32 launches of a step; the same restructuring does pay for bn_bwd_apply_kernel, which needs 5-11
+// per-channel vectors per element.)
 template <int RES_MODE>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ raw, long long rows, int C,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        Split res, const float* __restrict__ rawd,
                                                        const float* __restrict__ scaled, const float* __restrict__ shiftd,
                                                        int pitch25, Split out) {
-    const int C8 = C >> 3, rpi = 256 / C8;           // rows per block iteration
-    const int c = (threadIdx.x % C8) * 8, rl = threadIdx.x / C8;
-    float sc[8], sh[8], s2[8], h2[8];
-    load8(scale + c, sc); load8(shift + c, sh);
-    if (RES_MODE == 2) { load8(scaled + c, s2); load8(shiftd + c, h2); }
-    const long long stride = (long long)gridDim.x * rpi;
-    for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += 2 * stride) {
-        const long long rr[2] = {r0, r0 + stride};
-        float v[2][8], r[2][8];
-        bf16x8 rh[2], rlo[2];
-        bool live[2], valid[2];
+    const int C8 = C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * C8) return;
+    long long row = idx / C8;
+    int c = (int)(idx % C8) * 8;
+    size_t off = (size_t)row * C + c;
+    float o[8];
+    if (pitch25 && !p25_valid((int)(row % IMG25))) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            live[u] = rr[u] < rows;
-            valid[u] = live[u] && !(pitch25 && !p25_valid((int)(rr[u] % IMG25)));
-            const size_t off = (size_t)(live[u] ? rr[u] : r0) * C + c;
-            if (valid[u]) {
-                load8(raw + off, v[u]);
-                if (RES_MODE == 1) { rh[u] = *reinterpret_cast<const bf16x8*>(res.hi + off); rlo[u] = *reinterpret_cast<const bf16x8*>(res.lo + off); }
-                if (RES_MODE == 2) load8(rawd + off, r[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!live[u]) continue;
-            const size_t off = (size_t)rr[u] * C + c;
-            float o[8];
-            if (!valid[u]) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = 0.f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float x = fmaf(v[u][i], sc[i], sh[i]);
-                    if (RES_MODE == 1) x += bf2f(rh[u].v[i]) + bf2f(rlo[u].v[i]);
-                    if (RES_MODE == 2) x += fmaf(r[u][i], s2[i], h2[i]);
-                    o[i] = fmaxf(x, 0.f);
-                }
-            }
-            store8_split(out, off, o);
-        }
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        store8_split(out, off, o);
+        return;
     }
+    float v[8], sc[8], sh[8];
+    load8(raw + off, v); load8(scale + c, sc); load8(shift + c, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(v[i], sc[i], sh[i]);
+    if (RES_MODE == 1) {
+        float r[8];
+        load8_split(res, off, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r[i];
+    } else if (RES_MODE == 2) {
+        float r[8], s2[8], h2[8];
+        load8(rawd + off, r); load8(scaled + c, s2); load8(shiftd + c, h2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += fmaf(r[i], s2[i], h2[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+    store8_split(out, off, o);
 }
 
 int k_bn_apply(const float* raw, long long rows, int C, const float* scale, const float* shift, int res_mode,
                Split res, const float* rawd, const float* scaled, const float* shiftd, int pitch25, Split out,
                cudaStream_t s) {
-    if (C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0) { simq_set_error("k_bn_apply: C=%d", C); return 1; }
-    const int rpi = 256 / (C / 8);
-    long long want = (rows + 2 * rpi - 1) / (2 * rpi);          // at least two rows per thread where the problem allows
-    const int grid = (int)(want < 1 ? 1 : want > 8 * 148 ? 8 * 148 : want);
+    const long long n = rows * (C / 8);
+    const int grid = grid_for(n, 256);
     if (res_mode == 0) bn_apply_kernel<0><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
     else if (res_mode == 1) bn_apply_kernel<1><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
     else bn_apply_kernel<2><<<grid, 256, 0, s>>>(raw, rows, C, scale, shift, res, rawd, scaled, shiftd, pitch25, out);
@@ -975,7 +963,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            float inv_count, int pitch25, Split dy, float* __restrict__ dy_f32,
                                                            const float* __restrict__ rawd, const float* __restrict__ meand,
                                                            const float* __restrict__ invstdd, const float* __restrict__ gammad,
-                                                           Split dyd, float* dgamma, float* dbeta, float* dgammad, float* dbetad) {
+                                                           Split dyd, float* dgamma, float* dbeta, float* dgammad, float* dbetad, int hi_only) {
     const int C8 = C >> 3, rpi = 256 / C8;
     const int c = (threadIdx.x % C8) * 8, rl = threadIdx.x / C8;
     float s1[8], s2[8], mu[8], is[8], ga[8], sc[8], sh[8], s3[8], mud[8], isd[8], gad[8];
@@ -1027,8 +1015,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                     }
                 }
             }
-            if (dy_f32) store8(dy_f32 + off, o); else store8_split(dy, off, o);
-            if (HAS_DS) store8_split(dyd, off, od);
+            if (dy_f32) store8(dy_f32 + off, o); else if (hi_only) store8_hi(dy, off, o); else store8_split(dy, off, o);
+            if (HAS_DS) { if (hi_only) store8_hi(dyd, off, od); else store8_split(dyd, off, od); }
         }
     }
 }
@@ -1037,14 +1025,14 @@ int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const b
                    const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
                    const float* sums, double count, int pitch25, Split dy, float* dy_f32, const float* rawd,
                    const float* meand, const float* invstdd, const float* gammad, Split dyd, float* dgamma,
-                   float* dbeta, float* dgammad, float* dbetad, cudaStream_t s) {
+                   float* dbeta, float* dgammad, float* dbetad, int hi_only, cudaStream_t s) {
     if (C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0) { simq_set_error("k_bn_bwd_apply: C=%d", C); return 1; }
     const int rpi = 256 / (C / 8);
     long long want = (rows + 2 * rpi - 1) / (2 * rpi);
     const int grid = (int)(want < 1 ? 1 : want > 8 * 148 ? 8 * 148 : want);
     const float inv = (float)(1.0 / count);
 #define BWD_APPLY(MM, DS) bn_bwd_apply_kernel<MM, DS><<<grid, 256, 0, s>>>(G, rows, C, mask_hi, raw, scale, shift, mean, invstd, gamma, sums, inv, \
-        pitch25, dy, dy_f32, rawd, meand, invstdd, gammad, dyd, dgamma, dbeta, dgammad, dbetad)
+        pitch25, dy, dy_f32, rawd, meand, invstdd, gammad, dyd, dgamma, dbeta, dgammad, dbetad, hi_only)
     if (rawd) {
         if (mask_mode == 1) BWD_APPLY(1, true); else if (mask_mode == 2) BWD_APPLY(2, true); else BWD_APPLY(0, true);
     } else {

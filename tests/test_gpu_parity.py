@@ -32,9 +32,16 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 def test_conv_kernels_match_torch_fp64(backend, mode):
     from spatial_intention_maps_b200 import _lib
     ctx = _lib.Ctx(0, 4, 2, 3)
+    _lib.check(_lib.lib().simq_set_backward_terms(ctx.handle, 3, 3, 0), 'simq_set_backward_terms')     # the exact (three-term) kernels
     for (ci, co, k) in G.CONV_SHAPES:
         e = G.conv_check(ci, co, k, mode, backend, B=3, ctx=ctx)
         assert e < 2e-4, f'{ci}->{co} k{k} mode {mode} backend {backend}: rel err {e:.3e}'
+    if backend == 0 and mode > 0:
+        # two-term backward GEMMs (dy contributes its bf16 hi plane only): the error is dy's bf16 rounding, 2^-9 per element at most
+        _lib.check(_lib.lib().simq_set_backward_terms(ctx.handle, 2, 2, 0), 'simq_set_backward_terms')
+        for (ci, co, k) in G.CONV_SHAPES:
+            e = G.conv_check(ci, co, k, mode, backend, B=3, ctx=ctx)
+            assert 2e-4 < e < 4e-3, f'two-term {ci}->{co} k{k} mode {mode}: rel err {e:.3e}'
     ctx.close()
 
 
@@ -174,6 +181,20 @@ def test_gradients_against_float64_twin():
     for n, e in r['grad_rel_l2_64'].items():
         if r['grad_ref_norm'][n] >= 1e-6 * gn:
             assert e < max(1e-1, 10 * r['ref32_rel_l2_64'][n]), f'{n}: {e:.3e} (fp32 reference: {r["ref32_rel_l2_64"][n]:.3e})'
+
+
+def test_default_backward_terms_meet_the_acceptance_rule():
+    """The default backward scheme (weight gradients and layer-4 input gradients with two operand terms) was accepted under the
+    rule: every gradient / parameter bar unchanged, and the gradient error against the reference's float64 twin may grow by at
+    most 10 % over the three-term backward.  Re-measured here on c1 (measured: +5.9 %)."""
+    full = G.train_step_check(4, 2, 16, 11, 0.75, 8, 1, fused=True, with_fp64=True, setup=lambda p: p.set_backward_terms(3, 3, 0))
+    dflt = G.train_step_check(4, 2, 16, 11, 0.75, 8, 1, fused=True, with_fp64=True)
+    print('flat gradient rel-L2 vs float64: three-term backward %.4e, default %.4e (%+.1f %%), fp32 reference %.4e' % (
+        full['flat_grad_rel_l2_64'], dflt['flat_grad_rel_l2_64'], 100 * (dflt['flat_grad_rel_l2_64'] / full['flat_grad_rel_l2_64'] - 1),
+        dflt['flat_ref32_rel_l2_64']))
+    assert dflt['flat_grad_rel_l2_64'] <= 1.10 * full['flat_grad_rel_l2_64']
+    assert full['loss'] == dflt['loss']                      # the forward passes are untouched
+    _check_grads(dflt)
 
 
 def test_intention_step_matches_oracle_and_golden():
@@ -442,6 +463,7 @@ def test_pair_kernels_full_size_against_fma_comparator(mode):
     from spatial_intention_maps_b200 import _lib
     B, Ci, Co = 128, 512, 512
     ctx = _lib.Ctx(0, 4, 2, B)
+    _lib.check(_lib.lib().simq_set_backward_terms(ctx.handle, 3, 3, 0), 'simq_set_backward_terms')     # compare the exact kernels
     g = torch.Generator(device=G.DEV).manual_seed(5 + mode)
     a = torch.randn(B, Ci, 24, 24, device=G.DEV, generator=g)
     a2 = torch.randn(B, Co, 24, 24, device=G.DEV, generator=g) if mode == 2 else None
