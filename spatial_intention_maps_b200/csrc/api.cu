@@ -160,6 +160,7 @@ struct simq_ctx {
     cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     int* dev_err;                    // device error word (SIMQ_DEVERR_*), read by simq_check_device_errors
+    unsigned int* tickets;           // per-lane "CTAs finished" counters of the conv epilogues' fused statistics reduction (zero between launches)
     long long launch_total;          // kernels launched through this context (entry points credit their launches: LaunchScope)
     // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; long long launches; uint64_t last_use; };
@@ -283,6 +284,7 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->per_sample = carve<float>(c, B * 2, dry);
     c->best = carve<long long>(c, B, dry);
     c->dev_err = carve<int>(c, 64, dry);
+    c->tickets = carve<unsigned int>(c, 64, dry);
 }
 
 extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max_batch) {
@@ -412,11 +414,17 @@ struct Lane {
     float* partials;      // per-tile column sums of the conv / dgrad epilogues, colstats / bn_bwd_reduce partials
     float* scratch;       // split-K partials of small forward convs; wgrad split partials
     double* defer;        // non-NULL: train-mode BatchNorm stashes its running-statistics update here (see above)
+    unsigned int* ticket; // the lane's counter for the fused statistics reduction of its conv launches (ConvEpilogue::fin_ticket)
 };
-static Lane main_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials, c->wscratch2, nullptr}; }
-static Lane side_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials2, c->wscratch, nullptr}; }
+static bool fuse_stats_enabled() {      // SIMQ_FUSE_STATS=0: separate bn_finalize / reduce_partials launches (A/B experiments)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SIMQ_FUSE_STATS"); mode = e ? atoi(e) : 1; }
+    return mode != 0;
+}
+static Lane main_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials, c->wscratch2, nullptr, fuse_stats_enabled() ? c->tickets : nullptr}; }
+static Lane side_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, c->partials2, c->wscratch, nullptr, fuse_stats_enabled() ? c->tickets + 16 : nullptr}; }
 // eval-mode passes only: folded BatchNorm needs no column-sum partials
-static Lane eval_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, nullptr, c->wscratch3, nullptr}; }
+static Lane eval_lane(simq_ctx* c, cudaStream_t s) { return Lane{s, nullptr, c->wscratch3, nullptr, nullptr}; }
 
 static bool lanes_enabled(simq_ctx* c) {
     if (c->lanes_mode < 0) { const char* e = getenv("SIMQ_LANES"); c->lanes_mode = e ? (atoi(e) != 0) : 1; }
@@ -519,8 +527,25 @@ static int conv_bn(simq_ctx* c, ActSet& S, Split in, long long rows, int K, Spli
                    const Lane& L) {
     ConvEpilogue ep = conv_ep(pitch25);
     int nparts = 0;
-    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) { ep.stats = L.partials; ep.stat_rows_out = &nparts; }
+    bool fused = false;
+    if (training && c->backend == SIMQ_BACKEND_UMMA && umma_conv_supported(K, N)) {
+        ep.stats = L.partials; ep.stat_rows_out = &nparts;
+        if (L.ticket) {
+            // the last CTA of the conv launch does the BatchNorm bookkeeping (bn_finalize_train_kernel's arithmetic) itself
+            const NetDesc& d = c->d;
+            fused = true;
+            ep.fin_ticket = L.ticket; ep.fin_mode = 1; ep.fin_count = count;
+            ep.fin_gamma = params + d.poff[b.gamma]; ep.fin_beta = params + d.poff[b.gamma + 1];
+            ep.fin_bias = bias_param >= 0 ? params + d.poff[bias_param] : nullptr;
+            ep.fin_rmean = bn + d.bnoff[b.idx]; ep.fin_rvar = ep.fin_rmean + b.ch;
+            ep.fin_nbt = nbt ? (long long*)(nbt + b.idx) : nullptr;
+            ep.fin_defer = L.defer ? L.defer + (size_t)b.idx * 2 * MAX_CH : nullptr;
+            ep.fin_mean = bnstat(S, b.idx, BS_MEAN); ep.fin_invstd = bnstat(S, b.idx, BS_INVSTD);
+            ep.fin_scale = bnstat(S, b.idx, BS_SCALE); ep.fin_shift = bnstat(S, b.idx, BS_SHIFT);
+        }
+    }
     TRY(conv_any(c, c->backend, in, rows, K, W, N, ntaps, raw, ep, L));
+    if (fused) return 0;
     return bn_prepare(c, S, b, raw, rows, count, params, bn, nbt, bias_param, training, nparts, L);
 }
 
@@ -629,7 +654,9 @@ static int bn_backward(simq_ctx* c, ActSet& S, const BnP& b, const float* G, lon
                        float* dy_f32, const BnP* bd, const float* rawd, Split dyd, int nparts, const Lane& L, int hi_only = 0) {
     const NetDesc& d = c->d;
     cudaStream_t s = L.s;
-    if (nparts > 0) {
+    if (nparts < 0) {
+        // c->sums already holds (sum dz, sum dz*xhat): the dgrad launch that produced G reduced its partial rows itself
+    } else if (nparts > 0) {
         TRY(k_reduce_partials(L.partials, nparts, 2 * b.ch, c->sums, 1.0f, s));
     } else {
         TRY(k_bn_bwd_reduce(G, rows, b.ch, mask_mode, mask_hi, raw, bnstat(S, b.idx, BS_SCALE), bnstat(S, b.idx, BS_SHIFT),
@@ -717,11 +744,14 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
     // with a downsample branch need a third sum and keep the separate reduction.
     const bool fuse = be == SIMQ_BACKEND_UMMA;
-    int nparts_fused = 0;            // partial rows the last BN-sum-fusing dgrad launch wrote (ConvEpilogue::stat_rows_out)
+    int nparts_fused = 0;            // partial rows the last BN-sum-fusing dgrad launch wrote (ConvEpilogue::stat_rows_out);
+                                     // handed to bn_backward as -1 when that launch also reduced them into c->sums (fin_mode 2)
+    auto parts_of = [&](const ConvEpilogue& e) { return !e.bn_raw ? 0 : e.fin_ticket ? -1 : nparts_fused; };
     // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
     auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
         if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
             e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask; e.stat_rows_out = &nparts_fused;
+            if (M.ticket) { e.fin_ticket = M.ticket; e.fin_mode = 2; e.fin_out = c->sums; }
             e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
         }
         return e;
@@ -730,7 +760,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     {
         ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
         TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M, c->terms));
-        g_parts = e.bn_raw ? nparts_fused : 0;
+        g_parts = parts_of(e);
     }
     { float* t = G; G = Gn; Gn = t; }
     // ---- residual stages, last to first ----
@@ -754,7 +784,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         // b1 = relu(bn1(raw1))
         cur ^= 1; TRY(acquire(cur));
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
-                        none, em.bn_raw ? nparts_fused : 0, M, hi_only));
+                        none, parts_of(em), M, hi_only));
         TRY(wgrad_on_w(cur, dyA[cur], in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w]));
         // gradient w.r.t. the block input = the previous block's output (or the stem's pooled output for b == 0)
         const bool consumer_fusable = b > 0 && !d.blk[b - 1].has_ds;
@@ -763,13 +793,13 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         g_parts = 0;
         if (consumer_fusable && !P.has_ds) ep = with_bn_sums(ep, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes);
         TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s1], P.cin, 9, Gn, ep, M, dterms));
-        if (ep.bn_raw) g_parts = nparts_fused;            // (the launch has just reported its partial-row count)
+        if (ep.bn_raw) g_parts = parts_of(ep);            // (the launch has just reported its partial-row count)
         if (P.has_ds) {
             ConvEpilogue epd = ep25;
             epd.add_prev = Gn;
             if (consumer_fusable) epd = with_bn_sums(epd, d.blk[b - 1].b2, S.blk[b - 1].raw2, S.blk[b - 1].out.hi, P.cin, P.planes, 1);
             TRY(conv_any(c, be, c->dyB, R25, P.planes, pw->bwd[conv_slot(d, P.ds.w)], P.cin, 1, Gn, epd, M, dterms));
-            if (epd.bn_raw) g_parts = nparts_fused;
+            if (epd.bn_raw) g_parts = parts_of(epd);
         }
         { float* t = G; G = Gn; Gn = t; }
     }

@@ -81,6 +81,41 @@ __host__ __device__ inline void bilin_src(int dst, int in_size, int out_size, in
     w0 = 1.0f - w1;
 }
 
+// ---- nn.BatchNorm2d train-mode bookkeeping shared by bn_finalize_train_kernel and the conv epilogues' fused finalize ----
+#define SIMQ_BN_EPS 1e-5
+#define SIMQ_BN_MOM 0.1
+// running = (1 - momentum) * running + momentum * batch_value, with the rounding of every operation pinned (no
+// compiler-chosen FMA contraction): the immediate and the deferred update must agree bit for bit.
+__device__ __forceinline__ float bn_running_mix(float running, double batch_value) {
+    return (float)__dadd_rn(__dmul_rn(1.0 - SIMQ_BN_MOM, (double)running), __dmul_rn(SIMQ_BN_MOM, batch_value));
+}
+// One channel from its column sum S and sum of squares SS over `count` positions (eps 1e-5, momentum 0.1, unbiased variance into
+// running_var).  `raw` excludes the conv bias: the batch mean of the true conv output is mean_raw + bias, and the bias cancels in
+// the normalised value.  defer != NULL: a concurrent pass owns the running statistics, stash (mean + bias, unbiased var) instead.
+__device__ __forceinline__ void bn_finalize_channel(double S, double SS, double count, int c, const float* gamma, const float* beta,
+                                                    const float* conv_bias, float* rmean, float* rvar, double* defer, int defer_stride,
+                                                    float* mean, float* invstd, float* scale, float* shift) {
+    double m = S / count;
+    double var = SS / count - m * m;
+    if (var < 0) var = 0;
+    float is = (float)(1.0 / sqrt(var + SIMQ_BN_EPS));
+    float g = gamma[c], b = beta[c];
+    float bias = conv_bias ? conv_bias[c] : 0.f;
+    mean[c] = (float)m;
+    invstd[c] = is;
+    float sc = g * is;
+    scale[c] = sc;
+    shift[c] = b - (float)m * sc;
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    if (defer) {
+        defer[c] = m + (double)bias;
+        defer[defer_stride + c] = unbiased;
+        return;
+    }
+    rmean[c] = bn_running_mix(rmean[c], m + (double)bias);
+    rvar[c] = bn_running_mix(rvar[c], unbiased);
+}
+
 extern thread_local long long g_simq_launches;     // kernels launched by this library on the calling thread (host counter;
                                                    // api.cu credits the difference over an entry point to that call's context)
 void simq_set_error(const char* fmt, ...);

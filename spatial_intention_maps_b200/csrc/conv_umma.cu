@@ -320,6 +320,63 @@ __device__ __forceinline__ void flush_cta_stats(const float* csum, float* __rest
         stats[((size_t)row * 2 + which) * N + n0 + col] = csum[8 * BN + j];
     }
 }
+// The 4 epilogue warps of the LAST CTA to finish reduce the launch's partial rows [nrows][2][N] in row order (double accumulation,
+// 16 float4 loads in flight per thread) and do what the follow-up kernel used to do (ConvEpilogue::fin_mode).
+__device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, int N) {
+    const int t = threadIdx.x - 64;
+    const float* st = ep.stats;
+    for (int c0 = t * 4; c0 < N; c0 += 512) {
+        double S[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
+        int r = 0;
+        for (; r + 8 <= nrows; r += 8) {
+            float4 a[8], q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u) * 2 + 0) * N + c0));
+                q[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u) * 2 + 1) * N + c0));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                S[0] += a[u].x; S[1] += a[u].y; S[2] += a[u].z; S[3] += a[u].w;
+                Q[0] += q[u].x; Q[1] += q[u].y; Q[2] += q[u].z; Q[3] += q[u].w;
+            }
+        }
+        for (; r < nrows; ++r) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)r * 2 + 0) * N + c0));
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)r * 2 + 1) * N + c0));
+            S[0] += a.x; S[1] += a.y; S[2] += a.z; S[3] += a.w;
+            Q[0] += q.x; Q[1] += q.y; Q[2] += q.z; Q[3] += q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (ep.fin_mode == 1) {
+                bn_finalize_channel(S[i], Q[i], ep.fin_count, c0 + i, ep.fin_gamma, ep.fin_beta, ep.fin_bias, ep.fin_rmean, ep.fin_rvar,
+                                    ep.fin_defer, MAX_CH, ep.fin_mean, ep.fin_invstd, ep.fin_scale, ep.fin_shift);
+            } else {
+                ep.fin_out[c0 + i] = (float)S[i];
+                ep.fin_out[N + c0 + i] = (float)Q[i];
+            }
+        }
+    }
+    if (ep.fin_mode == 1 && t == 0 && ep.fin_nbt && !ep.fin_defer) ep.fin_nbt[0] += 1;
+}
+// after a CTA's last tile (epilogue warps only): publish its statistics, take a ticket, and finalize if it is the last one
+template <int BN>
+__device__ __forceinline__ void stats_tail(const ConvEpilogue& ep, float* csum, int stat_per_cta, bool has_tiles, int row, int n0, int N,
+                                           int nrows) {
+    if (stat_per_cta && has_tiles) flush_cta_stats<BN>(csum, ep.stats, row, n0, N);
+    if (!ep.fin_ticket) return;
+    __threadfence();                                   // this thread's partial sums are visible device-wide ...
+    epi_bar_sync();                                    // ... for all 128 epilogue threads, before the CTA takes its ticket
+    int* flag = reinterpret_cast<int*>(csum);          // (the per-warp area of csum is idle now)
+    if (threadIdx.x == 64) *flag = atomicAdd(ep.fin_ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    epi_bar_sync();
+    if (*flag) {
+        __threadfence();                               // acquire: every other CTA's rows were published before its ticket
+        stats_finalize(ep, nrows, N);
+        if (threadIdx.x == 64) *ep.fin_ticket = 0;     // ready for the next launch on this lane
+    }
+}
 
 template <int BN, int FL, int TERMS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -437,8 +494,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                                          out + (size_t)z * rows * N, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
-        if (stat_per_cta && (int)blockIdx.x < total_tiles)
-            flush_cta_stats<BN>(csum, ep.stats, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N);
+        if (HAS_STATS)
+            stats_tail<BN>(ep, csum, stat_per_cta, (int)blockIdx.x < total_tiles, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N,
+                           stat_per_cta ? (int)gridDim.x / n_tiles : m_tiles);
     }
     tc_fence_before();
     __syncthreads();
@@ -619,8 +677,9 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                                         out, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
-        if (stat_per_cta && cluster_id < total_tiles)
-            flush_cta_stats<BN>(csum, ep.stats, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N);
+        if (HAS_STATS)
+            stats_tail<BN>(ep, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
+                           stat_per_cta ? 2 * (num_clusters / n_tiles) : 2 * m2_tiles);
     }
     tc_fence_before();
     cluster_sync_all();             // nobody leaves while the peer may still touch its barriers / TMEM
@@ -812,8 +871,9 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                                         out, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
-        if (stat_per_cta && cluster_id < total_tiles)
-            flush_cta_stats<BN>(csum, ep.stats, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N);
+        if (HAS_STATS)
+            stats_tail<BN>(ep, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
+                           stat_per_cta ? 2 * (num_clusters / n_tiles) : 2 * m2_tiles);
     }
     tc_fence_before();
     cluster_sync_all();

@@ -94,6 +94,13 @@ struct ConvEpilogue {
     Split out_split;          // write v as split bf16 (out may then be NULL)
     float* stats;             // [stat rows][2][N] partial column sums / sums of squares of the raw accumulators
     int* stat_rows_out;       // (host) receives the number of partial rows the launch writes: one per CTA (<= 148) or one per m-tile
+    // Fused reduction of those partial rows by the LAST CTA of the launch to finish (ticket counter + fences; fixed row order, so the
+    // result does not depend on which CTA that is).  fin_mode 1: train-mode BatchNorm bookkeeping of the conv's output (what
+    // bn_finalize_train_kernel does); 2: plain column totals into fin_out[2][N] (what reduce_partials_kernel does for the
+    // BatchNorm-backward sums).  fin_ticket == NULL: no fused reduction, the caller launches those kernels.
+    unsigned int* fin_ticket; int fin_mode; double fin_count;
+    const float *fin_gamma, *fin_beta, *fin_bias; float *fin_rmean, *fin_rvar; long long* fin_nbt; double* fin_defer;
+    float *fin_mean, *fin_invstd, *fin_scale, *fin_shift, *fin_out;
     // BatchNorm-backward statistics of the gradient this launch produces (dgrad): with dz = out * [bn_mask > 0],
     // stats rows become (sum dz, sum dz * (bn_raw - mean) * invstd) -- saves the separate reduction pass
     const float* bn_raw; const bf16* bn_mask; const float* bn_mean; const float* bn_invstd;
@@ -107,6 +114,8 @@ static inline ConvEpilogue conv_ep(int pitch25) {
     e.res.hi = nullptr; e.res.lo = nullptr; e.relu = 0; e.out_split.hi = nullptr; e.out_split.lo = nullptr; e.stats = nullptr;
     e.bn_raw = nullptr; e.bn_mask = nullptr; e.bn_mean = nullptr; e.bn_invstd = nullptr; e.terms = 3;
     e.splitk_scratch = nullptr; e.splitk_floats = 0; e.stat_rows_out = nullptr;
+    e.fin_ticket = nullptr; e.fin_mode = 0; e.fin_count = 0; e.fin_gamma = e.fin_beta = e.fin_bias = nullptr; e.fin_rmean = e.fin_rvar = nullptr;
+    e.fin_nbt = nullptr; e.fin_defer = nullptr; e.fin_mean = e.fin_invstd = e.fin_scale = e.fin_shift = e.fin_out = nullptr;
     return e;
 }
 // out[m][n] = sum_t sum_k A[m+off_t][k] * W[t][n][k]   (A, W split bf16; fp32 accumulate)

@@ -47,12 +47,6 @@ int k_colstats(const float* x, long long rows, int C, float* partials, cudaStrea
     return 0;
 }
 
-// running = (1 - momentum) * running + momentum * batch_value, with the rounding of every operation pinned (no
-// compiler-chosen FMA contraction): the immediate and the deferred update must agree bit for bit.
-__device__ __forceinline__ float bn_running_mix(float running, double batch_value) {
-    return (float)__dadd_rn(__dmul_rn(1.0 - BN_MOM, (double)running), __dmul_rn(BN_MOM, batch_value));
-}
-
 // nn.BatchNorm2d train-mode bookkeeping (eps 1e-5, momentum 0.1, unbiased var into running_var,
 // num_batches_tracked += 1).  `raw` excludes the conv bias: the batch mean of the true conv output is
 // mean_raw + bias, and the bias cancels in the normalised value.
@@ -88,25 +82,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __
     S = 0; SS = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) { S += sS[i][cl]; SS += sSS[i][cl]; }
-    double m = S / count;
-    double var = SS / count - m * m;
-    if (var < 0) var = 0;
-    float is = (float)(1.0 / sqrt(var + BN_EPS));
-    float g = gamma[c], b = beta[c];
-    float bias = conv_bias ? conv_bias[c] : 0.f;
-    mean[c] = (float)m;
-    invstd[c] = is;
-    float sc = g * is;
-    scale[c] = sc;
-    shift[c] = b - (float)m * sc;
-    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    if (defer) {            // a concurrent pass owns the running statistics right now: bn_running_update_all applies these later
-        defer[c] = m + (double)bias;
-        defer[MAX_CH + c] = unbiased;
-        return;
-    }
-    rmean[c] = bn_running_mix(rmean[c], m + (double)bias);
-    rvar[c] = bn_running_mix(rvar[c], unbiased);
+    bn_finalize_channel(S, SS, count, c, gamma, beta, conv_bias, rmean, rvar, defer, MAX_CH, mean, invstd, scale, shift);
+    if (defer) return;      // a concurrent pass owns the running statistics right now: bn_running_update_all applies these later
     if (c == 0 && nbt) nbt[0] += 1;
 }
 
