@@ -95,19 +95,20 @@ def test_nchw_and_nhwc_inputs_agree():
 
 def _check_grads(r):
     """Gradients are ill-conditioned (ReLU / max-pool mask flips under rounding noise): the fp32
-    reference itself is 5e-3 rel-L2 away from its own float64 twin on the BN-bias gradients of c1.
-    Our operands carry 16 mantissa bits (bf16 hi+lo), so ~100x more pre-activations sit within rounding
-    noise of zero than in fp32.  Bars: whole gradient vector within 3e-2 rel-L2 of the reference, every
-    tensor within 1e-1, and
-    tensors whose true value is zero up to rounding (conv biases feeding a train-mode BN) within
-    1e-5 of the gradient norm in absolute terms."""
+    reference itself is 3e-3 .. 5e-3 rel-L2 away from its own float64 twin (profiles/r2_bwd_terms_probe.md,
+    r2_cstar128_gradient_probe.json).  Our operands carry 16 mantissa bits (bf16 hi+lo), so ~100x more pre-activations
+    sit within rounding noise of zero than in fp32.  Measured over every golden case, fused and autograd routes
+    (profiles/r2_v1_grad_errors_per_case.json): flat 1.2e-2 .. 2.8e-2 (worst: c* at batch 128), worst tensor 3.2e-2 =
+    7.8x the fp32 reference's own error on that tensor.  Bars: whole gradient vector within 3e-2 rel-L2 of the
+    reference, every tensor within 5e-2, and tensors whose true value is zero up to rounding (conv biases feeding a
+    train-mode BN) within 1e-5 of the gradient norm in absolute terms."""
     gn = r['grad_norm_ref']
     assert r['flat_grad_rel_l2'] < 3e-2, f"flat gradient rel-L2 {r['flat_grad_rel_l2']:.3e}"
     for n, e in r['grad_rel_l2'].items():
         if r['grad_ref_norm'][n] < 1e-6 * gn:
             assert r['grad_abs'][n] <= 1e-5 * gn, f'{n}: abs err {r["grad_abs"][n]:.3e}'
         else:
-            assert e < 1e-1, f'gradient {n} rel-L2 {e:.3e}'
+            assert e < 5e-2, f'gradient {n} rel-L2 {e:.3e}'
     assert abs(r['grad_norm'] - gn) <= 2e-3 * gn
 
 
