@@ -124,6 +124,17 @@ int simq_train_step(simq_ctx*, float* params, float* bn, int64_t* nbt, const flo
                     const float* reward, const uint8_t* nonfinal, int B, int Bn, float gamma, float lr,
                     float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
                     float* out2, simq_stream stream);
+/* The same step in two halves, for data-parallel callers that overlap the gradient all-reduce with the backward pass:
+ * phase 1 = forwards, tail, and the backward through the head and layer 4 -- when it has run, every gradient from
+ * resnet18.layer4.0.conv1.weight to the END of the flat vector (75 % of its bytes) is final; phase 2 = the rest of the
+ * backward (layers 3..1, stem) [+ the update if apply_update].  Phase 1 followed by phase 2 with the same arguments launches
+ * exactly the kernels of phase 0 (= simq_train_step): bit-identical results.  Each phase replays its own CUDA graph. */
+int simq_train_step_phase(simq_ctx*, float* params, float* bn, int64_t* nbt, const float* target_params,
+                          const float* target_bn, uint64_t target_version, float* grads, float* momentum,
+                          const float* s, const float* s_next, int x_layout, const int64_t* action,
+                          const float* reward, const uint8_t* nonfinal, int B, int Bn, float gamma, float lr,
+                          float mom, float wd, float clip_norm, int first_step, int double_dqn, int apply_update,
+                          float* out2, int phase, simq_stream stream);
 /* Optional, one-shot: `event` (a cudaEvent_t the caller records after the host->device copy of s_next, e.g. on a copy
  * stream) is what the NEXT simq_train_step waits for before anything reads s_next -- on the lane that runs the s'
  * passes only, so the copy of s' overlaps the forward on s (the reference uploads s' with non_blocking=True for the same

@@ -46,6 +46,9 @@ _PROTOS = {
     'simq_train_step': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, C.c_uint64, _p, _p, _p, _p, C.c_int, _p, _p, _p,
                                   C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_int, C.c_int, _p, _p]),
+    'simq_train_step_phase': (C.c_int, [_c_ctx, _p, _p, _p, _p, _p, C.c_uint64, _p, _p, _p, _p, C.c_int, _p, _p, _p,
+                                        C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_int, C.c_int, C.c_int, _p, C.c_int, _p]),
     'simq_set_next_state_event': (C.c_int, [_c_ctx, _p]),
     'simq_gather_rows': (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
     'simq_bce_tail': (C.c_int, [_c_ctx, _p, _p, C.c_int64, C.c_int64, _p, _p, _p]),

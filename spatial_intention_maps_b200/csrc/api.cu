@@ -160,6 +160,7 @@ struct simq_ctx {
     cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
     int* dev_err;                    // device error word (SIMQ_DEVERR_*), read by simq_check_device_errors
+    struct { int g_swapped, cur, g_parts; bool valid; } carry;      // backward state handed from phase 1 to phase 2 (simq_train_step_phase)
     unsigned int* tickets;           // per-lane "CTAs finished" counters of the conv epilogues' fused statistics reduction (zero between launches)
     long long launch_total;          // kernels launched through this context (entry points credit their launches: LaunchScope)
     // whole-step CUDA graphs (simq_train_step): one per distinct argument tuple, LRU of 8
@@ -337,7 +338,7 @@ extern "C" int simq_ctx_create(simq_ctx** out, int device, int C, int A, int max
             if (e != cudaSuccess) { simq_set_error("simq_ctx_create: table upload -> %s", cudaGetErrorString(e)); cudaFree(c->pool); delete c; return 1; }
         }
     }
-    c->launch_total = 0;
+    c->launch_total = 0; c->carry.valid = false;
     c->aux_stream = c->aux2_stream = nullptr; c->ev_next = 0; c->lanes_mode = -1; c->next_ready = nullptr;
     for (auto& e : c->ev_pool) e = nullptr;
     for (auto& e : c->ev_done) e = nullptr;
@@ -683,8 +684,11 @@ static int bias_grad(simq_ctx* c, Split dy, long long rows, int ch, float* out, 
 // saved activation, so it is handed to lane W.  The dy operand buffers are the hand-over points: dyA ping-pongs with dyA2
 // (lane M may fill the next dy while lane W still reads the previous one), and before any dy buffer is rewritten lane M
 // waits for the weight gradient that last read it (ev_done).  Lane W is joined before returning.
+// phase 0: the whole backward.  phase 1: head + layer 4 (after it -- lane W joined -- every gradient from
+// resnet18.layer4.0.conv1.weight to the end of the flat vector is final: 75 % of the bytes, which a data-parallel caller can
+// all-reduce while phase 2 runs); phase 2: layers 3..1 + stem.  1 followed by 2 launches exactly the kernels of 0.
 static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const float* x, int x_layout, const float* dq, int B,
-                        float* grads, cudaStream_t s) {
+                        float* grads, cudaStream_t s, int phase = 0) {
     const NetDesc& d = c->d;
     ActSet& S = c->set[0];
     if (!S.valid || !S.training || S.B != B) { simq_set_error("simq_fcn_backward: no matching training-mode saving forward (B=%d)", B); return 1; }
@@ -712,6 +716,34 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         if (two) { SIMQ_CUDA(cudaEventRecord(c->ev_done[buf], ws)); pending[buf] = true; }
         return 0;
     };
+    float* G = c->G[0];
+    float* Gn = c->G[1];
+    int g_parts = 0;                 // partial rows already available for the BN consuming G
+    ConvEpilogue ep25 = conv_ep(1);
+    // With the tcgen05 back-end the dgrad launch that PRODUCES a gradient also reduces the BatchNorm-backward sums of
+    // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
+    // with a downsample branch need a third sum and keep the separate reduction.
+    const bool fuse = be == SIMQ_BACKEND_UMMA;
+    int nparts_fused = 0;            // partial rows the last BN-sum-fusing dgrad launch wrote (ConvEpilogue::stat_rows_out);
+                                     // handed to bn_backward as -1 when that launch also reduced them into c->sums (fin_mode 2)
+    auto parts_of = [&](const ConvEpilogue& e) { return !e.bn_raw ? 0 : e.fin_ticket ? -1 : nparts_fused; };
+    // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
+    auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
+        if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
+            e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask; e.stat_rows_out = &nparts_fused;
+            if (M.ticket) { e.fin_ticket = M.ticket; e.fin_mode = 2; e.fin_out = c->sums; }
+            e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
+        }
+        return e;
+    };
+    const int PHASE_SPLIT_BLOCK = 5;                     // phase 1 ends after block 6 (layer4.0), phase 2 starts at block 5 (layer3.1)
+    if (phase == 2) {
+        if (!c->carry.valid) { simq_set_error("backward phase 2 without phase 1"); return 1; }
+        if (c->carry.g_swapped) { float* t = G; G = Gn; Gn = t; }
+        cur = c->carry.cur; g_parts = c->carry.g_parts;
+        c->carry.valid = false;
+    }
+    if (phase != 2) {
     // ---- head: upsample adjoint, conv3 + BN2 + conv2 ----
     TRY(k_up2_adj(dq, B, A, c->dt, s));
     const int hb2 = d.hbn2.idx;
@@ -732,39 +764,21 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     ConvEpilogue ep0 = conv_ep(0);
     TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M, c->terms));
     // ---- head: upsample adjoint, BN1 + conv1 ----
-    float* G = c->G[0];
-    float* Gn = c->G[1];
     TRY(k_up1_adj(c->du1, B, G, s));
     cur ^= 1; TRY(acquire(cur));
     TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr, none, 0, M));
     TRY(wgrad_on_w(cur, dyA[cur], S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w]));
     TRY(bias_grad(c, dyA[cur], R25, 128, grads + d.poff[d.h1_bias], M));
-    ConvEpilogue ep25 = conv_ep(1);
-    // With the tcgen05 back-end the dgrad launch that PRODUCES a gradient also reduces the BatchNorm-backward sums of
-    // the BN that will consume it (mask = sign of the saved activation, xhat from the saved raw conv output); blocks
-    // with a downsample branch need a third sum and keep the separate reduction.
-    const bool fuse = be == SIMQ_BACKEND_UMMA;
-    int nparts_fused = 0;            // partial rows the last BN-sum-fusing dgrad launch wrote (ConvEpilogue::stat_rows_out);
-                                     // handed to bn_backward as -1 when that launch also reduced them into c->sums (fin_mode 2)
-    auto parts_of = [&](const ConvEpilogue& e) { return !e.bn_raw ? 0 : e.fin_ticket ? -1 : nparts_fused; };
-    // (only where the main loop is long enough -- K*taps >= 2304 -- to hide the extra epilogue loads behind the MMAs)
-    auto with_bn_sums = [&](ConvEpilogue e, const BnP& bnp, const float* raw, const bf16* mask, int N, int K, int taps = 9) {
-        if (fuse && umma_conv_supported(K, N) && K * taps >= 2304) {
-            e.stats = M.partials; e.bn_raw = raw; e.bn_mask = mask; e.stat_rows_out = &nparts_fused;
-            if (M.ticket) { e.fin_ticket = M.ticket; e.fin_mode = 2; e.fin_out = c->sums; }
-            e.bn_mean = bnstat(S, bnp.idx, BS_MEAN); e.bn_invstd = bnstat(S, bnp.idx, BS_INVSTD);
-        }
-        return e;
-    };
-    int g_parts = 0;                 // partial rows already available for the BN consuming G
     {
         ConvEpilogue e = d.blk[7].has_ds ? ep25 : with_bn_sums(ep25, d.blk[7].b2, S.blk[7].raw2, S.blk[7].out.hi, 512, 128, 1);
         TRY(conv_any(c, be, dyA[cur], R25, 128, pw->bwd[conv_slot(d, d.h1.w)], 512, 1, Gn, e, M, c->terms));
         g_parts = parts_of(e);
     }
     { float* t = G; G = Gn; Gn = t; }
+    }   // phase != 2
     // ---- residual stages, last to first ----
-    for (int b = 7; b >= 0; --b) {
+    const int b_first = phase == 2 ? PHASE_SPLIT_BLOCK : 7, b_last = phase == 1 ? PHASE_SPLIT_BLOCK + 1 : 0;
+    for (int b = b_first; b >= b_last; --b) {
         const BlockP& P = d.blk[b];
         auto& Ab = S.blk[b];
         Split in = b == 0 ? S.a0 : S.blk[b - 1].out;
@@ -802,6 +816,11 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
             if (epd.bn_raw) g_parts = parts_of(epd);
         }
         { float* t = G; G = Gn; Gn = t; }
+    }
+    if (phase == 1) {
+        c->carry.g_swapped = G != c->G[0]; c->carry.cur = cur; c->carry.g_parts = g_parts; c->carry.valid = true;
+        TRY(lane_order(c, ws, s));                        // join: layer 4's and the head's weight gradients are final
+        return 0;
     }
     // ---- stem: maxpool + ReLU + BN + conv 7x7 ----
     const int sb = d.stem_bn.idx;
@@ -868,8 +887,19 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
                            const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
                            const float* s_next, int x_layout, const int64_t* action, const float* reward,
                            const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
-                           int first_step, int double_dqn, int apply_update, float* out2, cudaEvent_t next_ready, cudaStream_t s) {
+                           int first_step, int double_dqn, int apply_update, float* out2, cudaEvent_t next_ready, cudaStream_t s,
+                           int phase = 0) {
     int err;
+    if (phase == 2) {                          // the rest of the backward (layers 3..1, stem) of the step phase 1 started
+        PackedSet* pw2 = nullptr;
+        for (int i = 0; i < 2; ++i)
+            if (c->packed[i].used && c->packed[i].key == params) pw2 = &c->packed[i];
+        if (!pw2) { simq_set_error("simq_train_step_phase(2): no phase 1 on these parameters"); return 1; }
+        TRY(run_backward(c, pw2, params, s_, x_layout, c->dq, B, grads, s, 2));
+        if (apply_update)
+            TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
+        return 0;
+    }
     PackedSet* pw = get_packed(c, params, 0, s, &err);                                     // SGD changed them last step
     if (err) return 1;
     PackedSet* pt = nullptr;
@@ -932,8 +962,8 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
     TRY(k_dqn_tail(c->q_s, c->q_no, c->q_nt, (const long long*)action, reward, nonfinal, gamma, B, Bn, c->d.A, double_dqn,
                    c->per_sample, c->best, out2, dq, c->dev_err, s));
     // train.py:131-135
-    TRY(run_backward(c, pw, params, s_, x_layout, dq, B, grads, s));
-    if (apply_update)
+    TRY(run_backward(c, pw, params, s_, x_layout, dq, B, grads, s, phase));
+    if (apply_update && phase == 0)
         TRY(k_sgd_step(params, grads, momentum, c->d.poff.back(), lr, mom, wd, clip_norm, first_step, c->dpartials, nullptr, s));
     return 0;
 }
@@ -1029,12 +1059,13 @@ static void packed_set_version(simq_ctx* c, const float* params, uint64_t versio
         if (c->packed[i].used && c->packed[i].key == params) c->packed[i].version = version;
 }
 
-extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
-                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
-                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
-                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
-                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
+extern "C" int simq_train_step_phase(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                                     const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                                     const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                                     const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                                     int first_step, int double_dqn, int apply_update, float* out2, int phase, simq_stream stream) {
     TRY(check_fwd_args(c, params, bn, s_, B));
+    if (phase < 0 || phase > 2) { simq_set_error("simq_train_step_phase: phase %d", phase); return 1; }
     LaunchScope launch_scope(c);
     if (!target_params || !target_bn || !grads || !momentum || !action || !reward || !nonfinal || !out2) { simq_set_error("simq_train_step: NULL argument"); return 1; }
     if (Bn < 0 || Bn > B || (Bn > 0 && !s_next)) { simq_set_error("simq_train_step: Bn=%d", Bn); return 1; }
@@ -1044,19 +1075,30 @@ extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* n
                                  (uint64_t)target_hit, (uint64_t)grads, (uint64_t)momentum, (uint64_t)s_, (uint64_t)s_next, (uint64_t)x_layout,
                                  (uint64_t)action, (uint64_t)reward, (uint64_t)nonfinal, (uint64_t)B, (uint64_t)Bn, fbits(gamma), fbits(lr),
                                  fbits(mom), fbits(wd), fbits(clip_norm), (uint64_t)first_step, (uint64_t)double_dqn, (uint64_t)apply_update,
-                                 (uint64_t)out2, (uint64_t)c->next_ready};
-    cudaEvent_t next_ready = c->next_ready;
-    c->next_ready = nullptr;                                    // one-shot
+                                 (uint64_t)out2, (uint64_t)(phase == 2 ? nullptr : c->next_ready), (uint64_t)phase};
+    cudaEvent_t next_ready = phase == 2 ? nullptr : c->next_ready;
+    if (phase != 2) c->next_ready = nullptr;                    // one-shot
     return run_graphed(c, key, (cudaStream_t)stream,
         [&](cudaStream_t st) {
             return train_step_body(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout,
                                    action, reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update,
-                                   out2, next_ready, st);
+                                   out2, next_ready, st, phase);
         },
         [&]() {
-            if (Bn > 0) packed_set_version(c, target_params, target_version);
+            if (phase != 2 && Bn > 0) packed_set_version(c, target_params, target_version);
             c->set[0].valid = true; c->set[0].B = B; c->set[0].training = 1;
+            if (phase == 1) c->carry.valid = true;              // (the captured body filled the carry when the graph was built)
+            if (phase == 2) c->carry.valid = false;
         });
+}
+
+extern "C" int simq_train_step(simq_ctx* c, float* params, float* bn, int64_t* nbt, const float* target_params,
+                               const float* target_bn, uint64_t target_version, float* grads, float* momentum, const float* s_,
+                               const float* s_next, int x_layout, const int64_t* action, const float* reward,
+                               const uint8_t* nonfinal, int B, int Bn, float gamma, float lr, float mom, float wd, float clip_norm,
+                               int first_step, int double_dqn, int apply_update, float* out2, simq_stream stream) {
+    return simq_train_step_phase(c, params, bn, nbt, target_params, target_bn, target_version, grads, momentum, s_, s_next, x_layout, action,
+                                 reward, nonfinal, B, Bn, gamma, lr, mom, wd, clip_norm, first_step, double_dqn, apply_update, out2, 0, stream);
 }
 
 extern "C" int simq_set_next_state_event(simq_ctx* c, void* event) {

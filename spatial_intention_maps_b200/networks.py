@@ -302,6 +302,12 @@ class FCN(nn.Module):
             self._flat_grad = self._flat_grad_ext[:n]
         return self._flat_grad
 
+    def grad_bucket_split(self) -> int:
+        """Offset of ``resnet18.layer4.0.conv1.weight`` in the flat vectors: everything from there on is final after phase 1
+        of ``simq_train_step_phase`` (the backward runs head -> layer 4 -> ... -> stem)."""
+        names = [n for n, _ in self.trainable()]
+        return int(self._layout[2][names.index('resnet18.layer4.0.conv1.weight')])
+
     def flat_grad_ext(self) -> torch.Tensor:
         self.flat_grad()
         if getattr(self, '_flat_grad_ext', None) is None or self._flat_grad_ext.data_ptr() != self._flat_grad.data_ptr():

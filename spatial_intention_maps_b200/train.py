@@ -19,6 +19,7 @@ from __future__ import annotations
 from collections import namedtuple
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -28,6 +29,7 @@ from . import _lib
 from .networks import FCN
 
 Transition = namedtuple('Transition', ('state', 'action', 'reward', 'next_state'))     # train.py:26
+OVERLAP_ALLREDUCE = os.environ.get('SIMQ_OVERLAP_ALLREDUCE', '1') != '0'      # data parallel: all-reduce layer 4 + head under the rest of the backward
 
 
 def _unwrap(net) -> FCN:
@@ -240,14 +242,37 @@ def train_step_device(policy: FCN, target: FCN, optimizer, db: DeviceBatch, B: i
     ns_ready, db.ns_ready = getattr(db, 'ns_ready', None), None
     if ns_ready is not None:                 # s' is still on its way on the copy stream (DeviceBatch.upload)
         _lib.check(L.simq_set_next_state_event(ctx.handle, C.c_void_p(ns_ready.cuda_event)), 'simq_set_next_state_event')
-    _lib.check(L.simq_train_step(
-        ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(policy.flat_bn), _lib.ptr(policy.flat_nbt),
-        _lib.ptr(target.flat_params), _lib.ptr(target.flat_bn), target.params_version, _lib.ptr(grads),
-        _lib.ptr(policy.flat_momentum), _lib.ptr(db.s), _lib.ptr(db.ns), _lib.X_NHWC, _lib.ptr(db.action),
-        _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, float(discount_factor), lr, mom, wd, clip, first,
-        1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(out2), _lib.stream_ptr()), 'simq_train_step')
-    if world > 1:
-        allreduce_mean_(grads_ext, world)
+    def step(phase):
+        _lib.check(L.simq_train_step_phase(
+            ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(policy.flat_bn), _lib.ptr(policy.flat_nbt),
+            _lib.ptr(target.flat_params), _lib.ptr(target.flat_bn), target.params_version, _lib.ptr(grads),
+            _lib.ptr(policy.flat_momentum), _lib.ptr(db.s), _lib.ptr(db.ns), _lib.X_NHWC, _lib.ptr(db.action),
+            _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, float(discount_factor), lr, mom, wd, clip, first,
+            1 if use_double_dqn else 0, 1 if world == 1 else 0, _lib.ptr(out2), phase, _lib.stream_ptr()), 'simq_train_step')
+
+    if world == 1:
+        step(0)
+    else:
+        if OVERLAP_ALLREDUCE and dist.get_backend() == 'nccl':
+            # the backward retires layer 4 + head first: their gradients (75 % of the vector, and the report tail behind it) are
+            # all-reduced on a communication stream while phase 2 still computes the gradients of layers 3..1 and the stem
+            split = policy.grad_bucket_split()
+            comm = policy.__dict__.get('_comm_stream')
+            if comm is None:
+                comm = policy.__dict__['_comm_stream'] = torch.cuda.Stream(policy.flat_params.device)
+                policy.__dict__['_comm_event'] = torch.cuda.Event()
+            step(1)
+            ev = policy.__dict__['_comm_event']
+            ev.record()
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(grads_ext[split:], op=dist.ReduceOp.AVG)
+            step(2)
+            dist.all_reduce(grads_ext[:split], op=dist.ReduceOp.AVG)
+            torch.cuda.current_stream().wait_stream(comm)
+        else:
+            step(0)
+            allreduce_mean_(grads_ext, world)
         _lib.check(L.simq_sgd_step(ctx.handle, _lib.ptr(policy.flat_params), _lib.ptr(grads), _lib.ptr(policy.flat_momentum),
                                    lr, mom, wd, clip, first, None, _lib.stream_ptr()), 'simq_sgd_step')
         db.out2.copy_(out2, non_blocking=True)

@@ -562,3 +562,50 @@ def test_deepcopy_target_network_idiom():
             p.data.mul_(0.5)
         cp.mark_params_changed()                       # ... so the caller says so (Polyak-style updates)
         assert torch.equal(cp(x), net(x))
+
+
+def test_two_phase_step_is_bit_identical_to_the_whole_step():
+    """simq_train_step_phase: phase 1 (forwards, tail, backward through head + layer 4) followed by phase 2 (rest of the backward)
+    leaves exactly the gradients / BN statistics / report of the one-call step, eager and graph-replayed, and after phase 1 the
+    tail of the gradient vector (layer 4 + head) is already final -- what the data-parallel path all-reduces early."""
+    from spatial_intention_maps_b200 import _lib, networks, synth, train as T
+    L = _lib.lib()
+    B, C, A = 6, 5, 2
+    outs = []
+    for phased in (False, True):
+        net, st = G.make_net(C, A, 61, max_batch=B)
+        tgt = networks.FCN(C, A, max_batch=B)
+        tgt.load_state_dict(st)
+        tgt = tgt.to(G.DEV).eval()
+        net.train()
+        net.flat_momentum = torch.zeros_like(net.flat_params)
+        db = T.DeviceBatch(B, C, G.DEV).upload(T.HostBatch(B, C).fill(synth.synth_batch(B, C, A, 62, terminal_every=3)))
+        torch.cuda.synchronize()
+        grads, out2 = net.flat_grad(), torch.zeros(2, device=G.DEV)
+        split = net.grad_bucket_split()
+        tails = []
+
+        def call(phase):
+            _lib.check(L.simq_train_step_phase(
+                net.ctx(B).handle, _lib.ptr(net.flat_params), _lib.ptr(net.flat_bn), _lib.ptr(net.flat_nbt), _lib.ptr(tgt.flat_params),
+                _lib.ptr(tgt.flat_bn), tgt.params_version, _lib.ptr(grads), _lib.ptr(net.flat_momentum), _lib.ptr(db.s), _lib.ptr(db.ns),
+                _lib.X_NHWC, _lib.ptr(db.action), _lib.ptr(db.reward), _lib.ptr(db.nonfinal), B, db.Bn, 0.85, 0.01, 0.9, 1e-4, 100.0, 1, 1, 0,
+                _lib.ptr(out2), phase, _lib.stream_ptr()), 'simq_train_step_phase')
+        for rep in range(3):                                   # 1st call eager, 2nd captures, 3rd replays
+            grads.zero_()
+            if phased:
+                call(1)
+                torch.cuda.synchronize()
+                tails.append(grads[split:].clone())
+                call(2)
+            else:
+                call(0)
+            torch.cuda.synchronize()
+            outs.append((phased, rep, grads.clone(), net.flat_bn.clone(), net.flat_nbt.clone(), out2.clone()))
+            if phased:
+                assert torch.equal(tails[-1], grads[split:]) and float(grads[:split].abs().sum()) > 0
+    for rep in range(3):
+        a = next(o for o in outs if not o[0] and o[1] == rep)
+        b = next(o for o in outs if o[0] and o[1] == rep)
+        for i in range(2, 6):
+            assert torch.equal(a[i], b[i]), (rep, i)
