@@ -125,6 +125,7 @@ extern "C" int simq_layout(int C, int A, int64_t* n_params, int64_t* n_bn, int64
 // ------------------------------------------------------------------------------------------------
 struct ActSet {
     float* raw0; Split a0; Split acol;       // acol: im2col of the stem input [B*2304][Kp]
+    unsigned char* a0_amax;                  // saved set only: window position of every max-pool output's first maximum (pool_bwd_kernel)
     struct { float *raw1, *raw2, *rawd; Split b1, out; } blk[8];
     float* raw_h1; Split u1; float* raw_h2; float* t;
     float* bnstat;                   // [22][4][MAX_CH] : mean, invstd, scale, shift
@@ -218,6 +219,7 @@ static void carve_all(simq_ctx* c, bool dry) {
         const bool eval_only = s == 2;             // folded-BN passes never write raw1 / raw2 and borrow another set's im2col
         S.raw0 = carve<float>(c, R48 * 64, dry);
         S.a0 = carve_split(c, R25 * 64, dry);
+        S.a0_amax = s == 0 ? carve<unsigned char>(c, R25 * 64, dry) : nullptr;
         if (eval_only) { S.acol.hi = nullptr; S.acol.lo = nullptr; }
         else S.acol = carve_split(c, R48 * stem_kp(d.C), dry);
         for (int b = 0; b < 8; ++b) {
@@ -570,7 +572,7 @@ static int run_forward(simq_ctx* c, PackedSet* pw, const float* params, float* b
         TRY(k_stem_conv(x, x_layout, B, d.C, params + d.poff[d.stem.w], S.raw0, s));
         TRY(bn_prepare(c, S, d.stem_bn, S.raw0, R48, cnt48, params, bn, nbt, -1, training, 0, L));
     }
-    TRY(k_stem_pool(S.raw0, B, bnstat(S, d.stem_bn.idx, BS_SCALE), bnstat(S, d.stem_bn.idx, BS_SHIFT), S.a0, s));
+    TRY(k_stem_pool(S.raw0, B, bnstat(S, d.stem_bn.idx, BS_SCALE), bnstat(S, d.stem_bn.idx, BS_SHIFT), S.a0, training ? S.a0_amax : nullptr, s));
     // residual stages                                            (resnet.py:31-47, 99-102)
     Split in = S.a0;
     Split none{nullptr, nullptr};
@@ -824,7 +826,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     }
     // ---- stem: maxpool + ReLU + BN + conv 7x7 ----
     const int sb = d.stem_bn.idx;
-    TRY(k_pool_bwd(G, S.raw0, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
+    TRY(k_pool_bwd(G, S.raw0, S.a0_amax, B, bnstat(S, sb, BS_SCALE), bnstat(S, sb, BS_SHIFT), c->dz0, s));
     if (be == SIMQ_BACKEND_UMMA) {
         TRY(bn_backward(c, S, d.stem_bn, c->dz0, R48, cnt48, 0, nullptr, S.raw0, params, grads, 0, c->dy0s, nullptr, nullptr, nullptr, none, 0, M));
         TRY(wgrad_on_w(BUF_MISC, c->dy0s, S.acol, R48, 64, stem_kp(d.C), 1, c->stem_tmp));

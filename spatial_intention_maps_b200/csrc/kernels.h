@@ -21,7 +21,7 @@ int k_bn_eval_affine(int C, const float* gamma, const float* beta, const float* 
 int k_bn_apply(const float* raw, long long rows, int C, const float* scale, const float* shift, int res_mode,
                Split res, const float* rawd, const float* scaled, const float* shiftd, int pitch25, Split out,
                cudaStream_t s);
-int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift, Split a0, cudaStream_t s);
+int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift, Split a0, unsigned char* amax /* may be NULL */, cudaStream_t s);
 int k_head_up1(const float* raw_h1, int B, const float* scale, const float* shift, Split u1, cudaStream_t s);
 int k_head_t(const float* raw_h2, long long rows, const float* scale, const float* shift, const float* w3, int A,
              float* t, cudaStream_t s);
@@ -69,7 +69,7 @@ int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const b
                    const float* meand, const float* invstdd, const float* gammad, Split dyd, float* dgamma,
                    float* dbeta, float* dgammad, float* dbetad, int hi_only /* every consumer of dy is a two-term GEMM: skip the lo planes */,
                    cudaStream_t s);
-int k_pool_bwd(const float* g_a0, const float* raw0, int B, const float* scale, const float* shift, float* dz0,
+int k_pool_bwd(const float* g_a0, const float* raw0, const unsigned char* amax, int B, const float* scale, const float* shift, float* dz0,
                cudaStream_t s);
 int k_colsum_split(Split dy, long long rows, int C, float* partials, cudaStream_t s);   // bias grads: [STAT_BLOCKS][C]
 // head2 parameter gradients out of the reduced sums [2+2A][32]: dbeta2, dgamma2, dW3, db3

@@ -218,9 +218,11 @@ int k_bn_apply(const float* raw, long long rows, int C, const float* scale, cons
 }
 
 // stem: BN + ReLU + 3x3/2 max-pool (pad 1, -inf) : raw0 [B,48,48,64] -> a0 split pitch-25 (resnet.py:95-97)
+// amax (may be NULL): per output element the window position dy*3+dx of its FIRST maximum in scan order (ATen's max_pool2d rule),
+// kept by the differentiated pass so that the backward need not recompute the windows.
 __global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict__ raw0, int B,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        Split a0) {
+                                                        Split a0, unsigned char* __restrict__ amax) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * IMG25 * 8;
     if (idx >= total) return;
@@ -231,12 +233,14 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict_
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
         store8_split(a0, (size_t)p * 64 + c, o);
+        if (amax) *reinterpret_cast<uint2*>(amax + (size_t)p * 64 + c) = make_uint2(0xffffffffu, 0xffffffffu);     // halo: matches no position
         return;
     }
     float sc[8], sh[8];
     load8(scale + c, sc); load8(shift + c, sh);
+    unsigned char code[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = -INFINITY;
+    for (int i = 0; i < 8; ++i) { o[i] = -INFINITY; code[i] = 0; }
     for (int dy = 0; dy < 3; ++dy) {
         int iy = 2 * y - 1 + dy;
         if (iy < 0 || iy >= 48) continue;
@@ -246,15 +250,19 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict_
             float v[8];
             load8(raw0 + ((size_t)(n * 48 + iy) * 48 + ix) * 64 + c, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f));
+            for (int i = 0; i < 8; ++i) {
+                const float a = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
+                if (a > o[i]) { o[i] = a; code[i] = (unsigned char)(dy * 3 + dx); }      // strict: the first maximum wins
+            }
         }
     }
     store8_split(a0, (size_t)p * 64 + c, o);
+    if (amax) *reinterpret_cast<uint2*>(amax + (size_t)p * 64 + c) = *reinterpret_cast<const uint2*>(code);
 }
 
-int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift, Split a0, cudaStream_t s) {
+int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift, Split a0, unsigned char* amax, cudaStream_t s) {
     long long n = (long long)B * IMG25 * 8;
-    stem_pool_kernel<<<grid_for(n, 256), 256, 0, s>>>(raw0, B, scale, shift, a0);
+    stem_pool_kernel<<<grid_for(n, 256), 256, 0, s>>>(raw0, B, scale, shift, a0, amax);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
@@ -1021,10 +1029,12 @@ int k_bn_bwd_apply(const float* G, long long rows, int C, int mask_mode, const b
 }
 
 // stem: backward of 3x3/2 max-pool + ReLU: g_a0 pitch-25 [.,64] f32 -> dz0 dense [B,48,48,64] f32.
-// Gather form: an input pixel receives the gradient of every pooling window whose FIRST maximum (window
-// scan order, as ATen's max_pool2d) it is; ReLU gradient is zero where the activation is zero, so ties
-// among zeros cannot matter.
-__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ g_a0, const float* __restrict__ raw0, int B,
+// Gather form (no atomics): an input pixel receives the gradient of every pooling window whose FIRST maximum (window scan order, as
+// ATen's max_pool2d) it is -- the forward pass stored that position per output element (stem_pool_kernel's amax) -- and the ReLU
+// gradient is zero where the activation is zero, so ties among zeros cannot matter.  Per thread: its own raw value, and for each
+// of the <= 4 windows covering it 8 position bytes + 8 gradients (the first version recomputed every window: 36 loads per thread).
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ g_a0, const float* __restrict__ raw0,
+                                                       const unsigned char* __restrict__ amax, int B,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        float* __restrict__ dz0) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1044,37 +1054,23 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
     int ox_hi = (x + 1) / 2; if (ox_hi > 23) ox_hi = 23;
     for (int oy = oy_lo; oy <= oy_hi; ++oy)
         for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-            float best[8]; int besti[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; besti[i] = -1; }
-            for (int dy = 0; dy < 3; ++dy) {
-                int iy = 2 * oy - 1 + dy;
-                if (iy < 0 || iy >= 48) continue;
-                for (int dx = 0; dx < 3; ++dx) {
-                    int ix = 2 * ox - 1 + dx;
-                    if (ix < 0 || ix >= 48) continue;
-                    float v[8];
-                    load8(raw0 + ((size_t)(n * 48 + iy) * 48 + ix) * 64 + c, v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float a = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
-                        if (a > best[i]) { best[i] = a; besti[i] = iy * 48 + ix; }
-                    }
-                }
-            }
+            const size_t o = ((size_t)n * IMG25 + oy * PITCH + ox) * 64 + c;
+            const uint2 cw = *reinterpret_cast<const uint2*>(amax + o);
+            const unsigned char* code = reinterpret_cast<const unsigned char*>(&cw);
+            const unsigned char mine = (unsigned char)((y - (2 * oy - 1)) * 3 + (x - (2 * ox - 1)));      // this pixel's position in that window
             float g[8];
-            load8(g_a0 + ((size_t)n * IMG25 + oy * PITCH + ox) * 64 + c, g);
+            load8(g_a0 + o, g);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (besti[i] == y * 48 + x && self[i] > 0.f) acc[i] += g[i];
+                if (code[i] == mine && self[i] > 0.f) acc[i] += g[i];
         }
     store8(dz0 + (size_t)pos * 64 + c, acc);
 }
 
-int k_pool_bwd(const float* g_a0, const float* raw0, int B, const float* scale, const float* shift, float* dz0,
+int k_pool_bwd(const float* g_a0, const float* raw0, const unsigned char* amax, int B, const float* scale, const float* shift, float* dz0,
                cudaStream_t s) {
     long long n = (long long)B * 2304 * 8;
-    pool_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(g_a0, raw0, B, scale, shift, dz0);
+    pool_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(g_a0, raw0, amax, B, scale, shift, dz0);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
