@@ -707,32 +707,32 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 #define WIN_LEAD 26                                           // PITCH + 1: window row of tile row 0 at tap offset 0
 #define WIN_ROWS 184                                          // 128 + 2 * 26 = 180, rounded up to the 8-row swizzle atom
 
-template <int TERMS>
+template <int TERMS, int BN_ = 256>
 struct Conv2WCfg {
-    static constexpr int BN = 256;
+    static constexpr int BN = BN_;                            // pair tile: 256 rows x BN columns (256: stages 3-4; 128 / 64: stages 2 / 1)
     static constexpr int A_BYTES = WIN_ROWS * UM_BK * 2;      // one plane of this CTA's window (23 KB)
-    static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of one W tile, one plane (16 KB)
+    static constexpr int W_BYTES = (BN / 2) * UM_BK * 2;      // this CTA's half of one W tile, one plane (16 KB at BN = 256)
     static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;
     static constexpr int W_PLANES = TERMS >= 2 ? 2 : 1;
     static constexpr int A_BUFS = 2;
     static constexpr int A_BUF_BYTES = A_PLANES * A_BYTES;
     static constexpr int W_STAGE_BYTES = W_PLANES * W_BYTES;
-    static constexpr int W_STAGES = TERMS == 3 ? 3 : TERMS == 2 ? 4 : 6;
+    static constexpr int W_STAGES = BN < 256 ? 6 : TERMS == 3 ? 3 : TERMS == 2 ? 4 : 6;
     static constexpr int W_BASE = A_BUFS * A_BUF_BYTES;
     static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
     static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
     static constexpr int CSUM_BYTES = 5 * 2 * BN * 4;
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
     static constexpr int SMEM_BYTES = RING_BYTES + FIXED;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TMEM_COLS = 2 * BN;                  // two accumulators (power of two for every BN used)
 };
 
-template <int FL, int TERMS>
+template <int FL, int TERMS, int BN_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                    const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
                    int N, int m2_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
-    using Cfg = Conv2WCfg<TERMS>;
+    using Cfg = Conv2WCfg<TERMS, BN_>;
     constexpr int BN = Cfg::BN;
     static_assert(Cfg::A_BYTES % 1024 == 0, "window planes must keep the 1024-byte swizzle alignment");
     extern __shared__ uint8_t smem_raw[];
@@ -1296,11 +1296,16 @@ static int conv_window_mode() {      // SIMQ_CONV_WINDOW=0 falls back to the per
     if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW"); mode = e ? atoi(e) : 1; }
     return mode;
 }
-template <int FL, int TERMS>
+static int small_window_mode() {     // SIMQ_CONV_WINDOW_SMALL=0: stages 1-2 keep the single-CTA per-tap kernel (A/B experiments)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW_SMALL"); mode = e ? atoi(e) : 1; }
+    return mode;
+}
+template <int FL, int TERMS, int BN = 256>
 static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float* out, ConvEpilogue ep, cudaStream_t s) {
-    using Cfg = Conv2WCfg<TERMS>;
+    using Cfg = Conv2WCfg<TERMS, BN>;
     static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
-    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2w_umma_kernel<FL, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv2w_umma_kernel<FL, TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int g_num_sms = num_sms();
     CUtensorMap mAhi, mAlo, mWhi, mWlo;
     if (make_map(&mAhi, A.t.hi, A.rows, A.cols, WIN_ROWS) || make_map(&mAlo, A.t.lo, A.rows, A.cols, WIN_ROWS) ||
@@ -1312,7 +1317,7 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
     if (ep.stat_rows_out) *ep.stat_rows_out = clusters % n_tiles == 0 ? 2 * (clusters / n_tiles) : 2 * m2_tiles;    // see epilogue_tile
     const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
     prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * 9, s, 2.0 * TERMS * (double)A.rows * N * A.cols * 9);
-    conv2w_umma_kernel<FL, TERMS><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, m2_tiles, n_tiles,
+    conv2w_umma_kernel<FL, TERMS, BN><<<2 * clusters, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, m2_tiles, n_tiles,
                                                                          out, ep);
     prof_mark(PROF_CONV, false, 0, s);
     SIMQ_LAUNCH_CHECK();
@@ -1320,16 +1325,21 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
 }
 
 // the epilogue variants the network uses
-template <int BN, bool PAIR, int F, int TERMS>
+// PAIR: 0 = single-CTA 128 x BN tiles; 1 = CTA-pair 256 x 256 tiles (windowed for 3x3); 2 = windowed CTA-pair 256 x BN tiles, BN = 64 / 128
+// (3x3 convs of stages 1-2 on large batches: the per-tap A loads of the single-CTA kernel make those launches L2-bandwidth-bound --
+// 390 / 520 MB of L2 traffic per launch at ~10 TB/s -- while a window is loaded once per K chunk for all 9 taps)
+template <int BN, int PAIR, int F, int TERMS>
 static int conv_launch_t(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
-    if constexpr (PAIR) {
+    if constexpr (PAIR == 1) {
         if (ntaps == 9 && conv_window_mode() != 0) return launch_conv2w<F, TERMS>(A, W, N, out, ep, s);
         return launch_conv2<F, TERMS>(A, W, N, ntaps, out, ep, s);
+    } else if constexpr (PAIR == 2) {
+        return launch_conv2w<F, TERMS, BN>(A, W, N, out, ep, s);
     } else {
         return launch_conv<BN, F, TERMS>(A, W, N, ntaps, out, ep, s);
     }
 }
-template <int BN, bool PAIR, int F>
+template <int BN, int PAIR, int F>
 static int conv_by_terms(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     // the two-term variant exists for the epilogues dgrad launches use (raw fp32 output, +previous gradient, +masked identity
     // gradient, +BatchNorm-backward sums): the forward never runs it
@@ -1342,7 +1352,7 @@ static int conv_by_terms(const UmmaTensor& A, const UmmaTensor& W, int N, int nt
     }
     return conv_launch_t<BN, PAIR, F, 3>(A, W, N, ntaps, out, ep, s);
 }
-template <int BN, bool PAIR = false>
+template <int BN, int PAIR = 0>
 static int dispatch_conv(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     int fl = 0;
     if (ep.stats && !ep.bn_raw) fl |= EF_STATS;
@@ -1422,8 +1432,12 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         const long long t128 = (long long)ceil_div(A.rows, 128) * (N / 128), t256 = (long long)ceil_div(A.rows, 256) * (N / 256);
         const double cost_single = (double)((t128 + g_num_sms - 1) / g_num_sms);
         const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
-        if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, true>(A, W, N, ntaps, out, ep, s);
+        if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, 1>(A, W, N, ntaps, out, ep, s);
     }
+    // stages 1-2 (N = 64 / 128), 3x3, at least one round of the 74 CTA pairs: the windowed pair kernel with a 256 x N tile
+    if (ntaps == 9 && (N == 64 || N == 128) && policy != 1 && conv_window_mode() != 0 && small_window_mode() != 0 &&
+        ceil_div(A.rows, 256) >= num_sms() / 2)
+        return N == 128 ? dispatch_conv<128, 2>(A, W, N, ntaps, out, ep, s) : dispatch_conv<64, 2>(A, W, N, ntaps, out, ep, s);
     if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
     return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
 }

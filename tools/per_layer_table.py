@@ -6,8 +6,10 @@
 
     python tools/per_layer_table.py profiles/r1_v11_launches.csv [B_backward=128] [B_forward=126]
 
-Bound per launch = max(algorithmic FLOPs / parity-mode tensor ceiling, compulsory bytes / measured copy bandwidth); the
-fraction printed is bound time / measured time.  ncu per-launch times are cold-cache, serialised and NOT under the
+Bound per launch = max(algorithmic FLOPs / tensor ceiling of that launch, compulsory bytes / measured copy bandwidth); the
+fraction printed is bound time / measured time.  The tensor ceiling of a launch is the measured sustained bf16 peak divided by
+the MMAs it issues per algorithmic product: operand terms (3, or 2 for the weight-gradient GEMMs and the layer-4 input-gradient
+convolutions: last template argument of the kernel name) x 625/576 (pitch-25 halo rows).  ncu per-launch times are cold-cache, serialised and NOT under the
 steady-state power cap of the whole step: fractions above 1.0 against the SUSTAINED peak are expected for the big GEMMs.
 """
 import json
@@ -39,20 +41,32 @@ def is_gemm(n):
     return (('conv' in n and 'umma' in n) or n.startswith(('wgrad_umma', 'wgrad2_umma', 'wgrad_fma', 'conv_fma'))) and 'reduce' not in n
 
 
+def terms_of(kernel_name):
+    """Operand terms = last template argument of the tcgen05 kernels (conv*_umma_kernel<.., TERMS>, wgrad*_umma_kernel<.., TERMS>)."""
+    if '<' not in kernel_name:
+        return 3
+    try:
+        return int(kernel_name[kernel_name.index('<') + 1:kernel_name.rindex('>')].split(',')[-1])
+    except ValueError:
+        return 3
+
+
 def emit(title, layers, launches):
     assert len(layers) == len(launches), (title, len(layers), len(launches))
     print(f'\n### {title}\n')
-    print('| layer | kernel | us | TFLOP/s (algorithmic) | of parity-mode tensor ceiling %.0f | GB/s (compulsory bytes) | of %.0f GB/s | binding: bound / measured |' % (CEIL, HBM))
-    print('|---|---|---|---|---|---|---|---|')
+    print('| layer | kernel | terms | us | TFLOP/s (algorithmic) | of its tensor ceiling (%.0f at 3 terms, %.0f at 2) | GB/s (compulsory bytes) | of %.0f GB/s | binding: bound / measured |' % (CEIL, CEIL * 1.5, HBM))
+    print('|---|---|---|---|---|---|---|---|---|')
     tt = tb = tf = 0.0
     for (name, fl, byts), (kn, t) in zip(layers, launches):
+        terms = terms_of(kn)
+        ceil = PEAK * 576 / (terms * 625)
         tfl, gbs = fl / (t * 1e-3) / 1e12, byts / (t * 1e-3) / 1e9
-        t_tensor, t_hbm = fl / (CEIL * 1e12) * 1e3, byts / (HBM * 1e9) * 1e3          # ms
+        t_tensor, t_hbm = fl / (ceil * 1e12) * 1e3, byts / (HBM * 1e9) * 1e3          # ms
         bound = max(t_tensor, t_hbm)
         tt += t; tb += bound; tf += fl
-        print(f'| {name} | `{kn.split("<")[0]}` | {t * 1e3:.1f} | {tfl:.0f} | {tfl / CEIL:.2f} | {gbs:.0f} | {gbs / HBM:.2f} | '
+        print(f'| {name} | `{kn.split("<")[0]}` | {terms} | {t * 1e3:.1f} | {tfl:.0f} | {tfl / ceil:.2f} | {gbs:.0f} | {gbs / HBM:.2f} | '
               f'{"tensor" if t_tensor >= t_hbm else "HBM"}: **{bound / t:.2f}** |')
-    print(f'| all {len(layers)} launches | | {tt * 1e3:.0f} | {tf / (tt * 1e-3) / 1e12:.0f} | {tf / (tt * 1e-3) / 1e12 / CEIL:.2f} | | | time-weighted: **{tb / tt:.2f}** |')
+    print(f'| all {len(layers)} launches | | | {tt * 1e3:.0f} | {tf / (tt * 1e-3) / 1e12:.0f} | | | | time-weighted: **{tb / tt:.2f}** |')
     return tt, tb
 
 
@@ -62,7 +76,7 @@ def conv_entry(name, cin, cout, taps, pix, rows_in, k_eff=None):
 
 
 # ---------------- forward ----------------
-start = next(i for i, n in enumerate(names) if n.startswith('stem_im2col_kernel'))
+start = next(i for i, n in enumerate(names) if n.startswith('stem_im2col'))
 end = names.index('head_up2_kernel', start)
 fwd = [(n, t) for n, t, _ in rows[start:end] if is_gemm(n)]
 L = [conv_entry('stem conv1 7x7/2 as GEMM (K=245 padded to 256)', 256, 64, 1, BF * 2304, BF * 2304, 245)]
@@ -72,7 +86,7 @@ for cin, planes, ds in STAGES:
     if ds:
         L.append(conv_entry(f'downsample 1x1 {cin}->{planes}', cin, planes, 1, BF * 576, BF * 625))
 L += [conv_entry('head conv1 1x1 512->128', 512, 128, 1, BF * 576, BF * 625), conv_entry('head conv2 1x1 128->32 at 48x48', 128, 32, 1, BF * 2304, BF * 2304)]
-print(f'Peaks: measured sustained bf16 {PEAK:.0f} TFLOP/s -> parity-mode ceiling {CEIL:.0f} (3 MMAs per product, 625/576 padding); copy bandwidth {HBM:.0f} GB/s.')
+print(f'Peaks: measured sustained bf16 {PEAK:.0f} TFLOP/s -> tensor ceiling {CEIL:.0f} at 3 MMAs per product, {CEIL * 1.5:.0f} at 2 (625/576 halo padding included); copy bandwidth {HBM:.0f} GB/s.')
 ft, fb = emit(f'Train-mode forward (B = {BF})', L, fwd)
 
 # ---------------- backward ----------------
@@ -95,7 +109,7 @@ def dg(name, cout, cin, taps, pix, rows_):   # dY [rows][cout] -> dX [rows][cin]
 
 
 P24, R25, P48 = B * 576, B * 625, B * 2304
-Lb = [wg('wgrad head conv2 (32 x 128, FMA: below the tensor tile)', 32, 128, 1, P48, P48), dg('dgrad head conv2 (FMA)', 32, 128, 1, P48, P48),
+Lb = [wg('wgrad head conv2 (32 x 128, dy zero-padded to 64 channels)', 32, 128, 1, P48, P48), dg('dgrad head conv2 (K zero-padded to 64)', 32, 128, 1, P48, P48),
       wg('wgrad head conv1 128 x 512 1x1', 128, 512, 1, P24, R25), dg('dgrad head conv1 128->512 1x1', 128, 512, 1, P24, R25)]
 for cin, planes, ds in reversed(STAGES):
     Lb.append(wg(f'wgrad conv2 {planes} x {planes} 3x3', planes, planes, 9, P24, R25))
