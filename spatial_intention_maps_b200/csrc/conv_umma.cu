@@ -123,6 +123,14 @@ __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 
 #define UM_BK 64
 #define UM_THREADS 192          // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
 
+// true in exactly one lane of a converged warp (elect.sync): the MMA warp runs its loop warp-wide -- every lane waits on the
+// barriers -- and only the elected lane issues; ptxas then predicates the tcgen05 instructions instead of wrapping each one in a
+// "for every active lane" loop, which is what a divergent `if (lane == 0)` region costs (5 extra instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -442,7 +450,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp walks the loop (every lane waits on the barriers), one elected lane issues: see elect_one()
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
@@ -454,28 +462,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                    // one descriptor per operand plane; the K = 16 steps advance its start-address field ((addr >> 4), no carry: smem < 256 KB)
+                    const uint64_t a_hi0 = umma_desc(sa, 16, Cfg::SBO, Cfg::LAYOUT), w_hi0 = umma_desc(sa + Cfg::W_OFF, 16, Cfg::SBO, Cfg::LAYOUT);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t w_hi = umma_desc(sa + Cfg::W_OFF + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        if (TERMS == 3) {
-                            const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                            tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
-                            tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
-                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
-                        } else if (TERMS == 2) {
-                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                            tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
-                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
-                        } else {
-                            tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
+                            if (TERMS == 3) {
+                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else if (TERMS == 2) {
+                                const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else {
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                            }
                         }
+                        tc_commit(empty_bar(s));        // frees the stage once these MMAs have read it
+                        if (it == iters - 1) tc_commit(tfull_bar(acc));
                     }
-                    tc_commit(empty_bar(s));            // frees the stage once these MMAs have read it
+                    __syncwarp();
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; aph ^= 1u; }
             }
         }
@@ -626,7 +637,7 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {            // warp-wide loop, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc(256, BN, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
@@ -638,28 +649,30 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                    const uint64_t a_hi0 = umma_desc(sa, 16, 1024), w_hi0 = umma_desc(sa + Cfg::W_OFF, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < UM_BK / 16; ++k) {
-                        const uint64_t a_hi = umma_desc(sa + k * 32, 16, 1024);
-                        const uint64_t w_hi = umma_desc(sa + Cfg::W_OFF + k * 32, 16, 1024);
-                        if (TERMS == 3) {
-                            const uint64_t a_lo = umma_desc(sa + Cfg::A_BYTES + k * 32, 16, 1024);
-                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, 1024);
-                            tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
-                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
-                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
-                        } else if (TERMS == 2) {
-                            const uint64_t w_lo = umma_desc(sa + Cfg::W_OFF + Cfg::W_BYTES + k * 32, 16, 1024);
-                            tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
-                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
-                        } else {
-                            tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                        for (int k = 0; k < UM_BK / 16; ++k) {
+                            const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
+                            if (TERMS == 3) {
+                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
+                                tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
+                                tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else if (TERMS == 2) {
+                                const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
+                                tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else {
+                                tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
+                            }
                         }
+                        tc_commit_mc2(empty_bar(s));
+                        if (it == iters - 1) tc_commit_mc2(tfull_bar(acc));
                     }
-                    tc_commit_mc2(empty_bar(s));
+                    __syncwarp();
                     if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
                 }
-                tc_commit_mc2(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; aph ^= 1u; }
             }
         }
@@ -808,7 +821,7 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc(256, BN, 0, 0);
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
@@ -828,19 +841,22 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                     mbar_wait(wfull_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
+                    // descriptors of the K = 16 steps / lo planes differ from the first one only in the start-address field
+                    // ((addr >> 4) in the low bits; shared memory is < 256 KB, so the field cannot carry): one add per descriptor
+                    // instead of rebuilding it -- the issuing thread is the bottleneck of the narrow tiles (N <= 128)
+                    const uint64_t a_hi0 = umma_desc(arow, 16, 1024), w_hi0 = umma_desc(sw, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < UM_BK / 16; ++k) {
-                        const uint64_t a_hi = umma_desc(arow + k * 32, 16, 1024);
-                        const uint64_t w_hi = umma_desc(sw + k * 32, 16, 1024);
+                        const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
                         const uint32_t accumulate = (kc | t | k) != 0;
                         if (TERMS == 3) {
-                            const uint64_t a_lo = umma_desc(arow + Cfg::A_BYTES + k * 32, 16, 1024);
-                            const uint64_t w_lo = umma_desc(sw + Cfg::W_BYTES + k * 32, 16, 1024);
+                            const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
                             tc_mma_bf16_cg2(d_tmem, a_lo, w_hi, idesc, accumulate);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, 1);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
                         } else if (TERMS == 2) {
-                            const uint64_t w_lo = umma_desc(sw + Cfg::W_BYTES + k * 32, 16, 1024);
+                            const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_lo, idesc, accumulate);
                             tc_mma_bf16_cg2(d_tmem, a_hi, w_hi, idesc, 1);
                         } else {
@@ -848,11 +864,16 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                         }
                     }
                     tc_commit_mc2(wempty_bar(s));
+                    }
+                    __syncwarp();
                     if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
                 }
-                tc_commit_mc2(aempty_bar(b));                    // the window is free once the 9 taps have read it
+                if (elect_one()) {
+                    tc_commit_mc2(aempty_bar(b));                // the window is free once the 9 taps have read it
+                    if (kc == kchunks - 1) tc_commit_mc2(tfull_bar(acc));
+                }
+                __syncwarp();
                 if (kc == kchunks - 1) {
-                    tc_commit_mc2(tfull_bar(acc));
                     if (++acc == 2) { acc = 0; aph ^= 1u; }
                 }
             }
@@ -956,37 +977,39 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // warp-wide loop, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 1, 1);
             int s = 0; uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                // MN-major SWIZZLE_128B: 8 rows of 128 B per atom (SBO = 1024 B between 8-row groups along
+                // K), 64-channel blocks 8 KB apart (LBO); a K=16 step is two atoms = 2048 B (= +128 in the start-address field).
+                const uint64_t y_hi0 = umma_desc(sa, 8192, 1024), x_hi0 = umma_desc(sa + Cfg::B_OFF, 8192, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < UM_BK / 16; ++k) {
-                    // MN-major SWIZZLE_128B: 8 rows of 128 B per atom (SBO = 1024 B between 8-row groups along
-                    // K), 64-channel blocks 8 KB apart (LBO); a K=16 step is two atoms = 2048 B.
-                    const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t x_hi = umma_desc(sa + Cfg::B_OFF + k * 2048, 8192, 1024);
-                    if (TERMS == 3) {
-                        const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
-                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
-                        tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
-                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
-                    } else if (TERMS == 2) {
-                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
-                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
-                    } else {
-                        tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t y_hi = y_hi0 + (uint64_t)(k * 128), x_hi = x_hi0 + (uint64_t)(k * 128);
+                        if (TERMS == 3) {
+                            const uint64_t y_lo = y_hi + (uint64_t)(Cfg::A_BYTES >> 4), x_lo = x_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                            tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
+                            tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
+                            tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                        } else if (TERMS == 2) {
+                            const uint64_t x_lo = x_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                            tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
+                            tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, 1);
+                        } else {
+                            tc_mma_bf16(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                        }
                     }
+                    tc_commit(empty_bar(s));
+                    if (it == iters - 1) tc_commit(accum_bar);
                 }
-                tc_commit(empty_bar(s));
+                __syncwarp();
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
-            tc_commit(accum_bar);
         }
     } else {
         const int quad = warp & 3;
@@ -1084,35 +1107,37 @@ wgrad2_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {            // warp-wide loop, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc(256, 256, 1, 1);
             int s = 0; uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+                const uint64_t y_hi0 = umma_desc(sa, 8192, 1024), x_hi0 = umma_desc(sa + Cfg::B_OFF, 8192, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < UM_BK / 16; ++k) {
-                    const uint64_t y_hi = umma_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t x_hi = umma_desc(sa + Cfg::B_OFF + k * 2048, 8192, 1024);
-                    if (TERMS == 3) {
-                        const uint64_t y_lo = umma_desc(sa + Cfg::A_BYTES + k * 2048, 8192, 1024);
-                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        tc_mma_bf16_cg2(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
-                        tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, 1);
-                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
-                    } else if (TERMS == 2) {
-                        const uint64_t x_lo = umma_desc(sa + Cfg::B_OFF + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
-                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
-                    } else {
-                        tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t y_hi = y_hi0 + (uint64_t)(k * 128), x_hi = x_hi0 + (uint64_t)(k * 128);
+                        if (TERMS == 3) {
+                            const uint64_t y_lo = y_hi + (uint64_t)(Cfg::A_BYTES >> 4), x_lo = x_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                            tc_mma_bf16_cg2(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
+                            tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, 1);
+                            tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
+                        } else if (TERMS == 2) {
+                            const uint64_t x_lo = x_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                            tc_mma_bf16_cg2(tmem_base, y_hi, x_lo, idesc, (it | k) != 0);
+                            tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, 1);
+                        } else {
+                            tc_mma_bf16_cg2(tmem_base, y_hi, x_hi, idesc, (it | k) != 0);
+                        }
                     }
+                    tc_commit_mc2(empty_bar(s));
+                    if (it == iters - 1) tc_commit_mc2(accum_bar);
                 }
-                tc_commit_mc2(empty_bar(s));
+                __syncwarp();
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
             }
-            tc_commit_mc2(accum_bar);
         }
     } else {
         const int quad = warp & 3;
