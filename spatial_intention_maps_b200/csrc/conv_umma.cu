@@ -1321,11 +1321,6 @@ static int conv_window_mode() {      // SIMQ_CONV_WINDOW=0 falls back to the per
     if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW"); mode = e ? atoi(e) : 1; }
     return mode;
 }
-static int small_window_mode() {     // SIMQ_CONV_WINDOW_SMALL=0: stages 1-2 keep the single-CTA per-tap kernel (A/B experiments)
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW_SMALL"); mode = e ? atoi(e) : 1; }
-    return mode;
-}
 template <int FL, int TERMS, int BN = 256>
 static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float* out, ConvEpilogue ep, cudaStream_t s) {
     using Cfg = Conv2WCfg<TERMS, BN>;
@@ -1350,16 +1345,12 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
 }
 
 // the epilogue variants the network uses
-// PAIR: 0 = single-CTA 128 x BN tiles; 1 = CTA-pair 256 x 256 tiles (windowed for 3x3); 2 = windowed CTA-pair 256 x BN tiles, BN = 64 / 128
-// (3x3 convs of stages 1-2 on large batches: the per-tap A loads of the single-CTA kernel make those launches L2-bandwidth-bound --
-// 390 / 520 MB of L2 traffic per launch at ~10 TB/s -- while a window is loaded once per K chunk for all 9 taps)
+// PAIR: 0 = single-CTA 128 x BN tiles; 1 = CTA-pair 256 x 256 tiles (windowed for 3x3)
 template <int BN, int PAIR, int F, int TERMS>
 static int conv_launch_t(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     if constexpr (PAIR == 1) {
         if (ntaps == 9 && conv_window_mode() != 0) return launch_conv2w<F, TERMS>(A, W, N, out, ep, s);
         return launch_conv2<F, TERMS>(A, W, N, ntaps, out, ep, s);
-    } else if constexpr (PAIR == 2) {
-        return launch_conv2w<F, TERMS, BN>(A, W, N, out, ep, s);
     } else {
         return launch_conv<BN, F, TERMS>(A, W, N, ntaps, out, ep, s);
     }
@@ -1459,10 +1450,11 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
         if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, 1>(A, W, N, ntaps, out, ep, s);
     }
-    // stages 1-2 (N = 64 / 128), 3x3, at least one round of the 74 CTA pairs: the windowed pair kernel with a 256 x N tile
-    if (ntaps == 9 && (N == 64 || N == 128) && policy != 1 && conv_window_mode() != 0 && small_window_mode() != 0 &&
-        ceil_div(A.rows, 256) >= num_sms() / 2)
-        return N == 128 ? dispatch_conv<128, 2>(A, W, N, ntaps, out, ep, s) : dispatch_conv<64, 2>(A, W, N, ntaps, out, ep, s);
+    // (The windowed pair kernel with 256 x 128 / 256 x 64 tiles was built for the 3x3 convs of stages 1-2 -- whose per-tap A loads
+    // make the single-CTA kernel L2-bandwidth-bound, 390 / 520 MB of L2 traffic per launch at ~10 TB/s -- and measured: L2 traffic
+    // -67 %, but SS-mode MMAs re-read the 128 x 16 A slice from shared memory for every instruction, 6 KB per 32 tensor cycles at
+    // N = 128 and 5 KB per 16 at N = 64 against 128 B/clk of shared-memory bandwidth, so the launches got SLOWER (67 vs 50 us, 41 vs
+    // 39 us) and the step did not move: dropped.  DESIGN.md section 9.)
     if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
     return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
 }
