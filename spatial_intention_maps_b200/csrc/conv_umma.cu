@@ -328,20 +328,25 @@ __device__ __forceinline__ void flush_cta_stats(const float* csum, float* __rest
         stats[((size_t)row * 2 + which) * N + n0 + col] = csum[8 * BN + j];
     }
 }
-// The 4 epilogue warps of the LAST CTA to finish reduce the launch's partial rows [nrows][2][N] in row order (double accumulation,
-// 16 float4 loads in flight per thread) and do what the follow-up kernel used to do (ConvEpilogue::fin_mode).
-__device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, int N) {
+// The 4 epilogue warps of the LAST CTA to finish reduce the launch's partial rows [nrows][2][N] (double accumulation) and do what
+// the follow-up kernel used to do (ConvEpilogue::fin_mode).  Thread t owns float4 column group t % (N/4) and row group t / (N/4):
+// narrow layers (N = 64: 16 column groups) split the rows over 8 row groups, so every thread has loads in flight; the row groups
+// are combined through shared memory in group order.  Everything is a fixed order: the result does not depend on which CTA this is.
+__device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, int N, double* red /* >= 128 * 8 doubles */) {
     const int t = threadIdx.x - 64;
     const float* st = ep.stats;
-    for (int c0 = t * 4; c0 < N; c0 += 512) {
-        double S[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
-        int r = 0;
-        for (; r + 8 <= nrows; r += 8) {
+    const int cgs = N >> 2;                            // float4 column groups: 8 .. 128
+    const int rgs = cgs >= 128 ? 1 : 128 / cgs;        // row groups
+    const int cg = t % cgs, rg = t / cgs, c0 = cg * 4;
+    double S[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
+    if (rg < rgs) {
+        int r = rg;
+        for (; r + 7 * rgs < nrows; r += 8 * rgs) {
             float4 a[8], q[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                a[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u) * 2 + 0) * N + c0));
-                q[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u) * 2 + 1) * N + c0));
+                a[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u * rgs) * 2 + 0) * N + c0));
+                q[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u * rgs) * 2 + 1) * N + c0));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -349,12 +354,29 @@ __device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, i
                 Q[0] += q[u].x; Q[1] += q[u].y; Q[2] += q[u].z; Q[3] += q[u].w;
             }
         }
-        for (; r < nrows; ++r) {
+        for (; r < nrows; r += rgs) {
             const float4 a = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)r * 2 + 0) * N + c0));
             const float4 q = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)r * 2 + 1) * N + c0));
             S[0] += a.x; S[1] += a.y; S[2] += a.z; S[3] += a.w;
             Q[0] += q.x; Q[1] += q.y; Q[2] += q.z; Q[3] += q.w;
         }
+    }
+    if (rgs > 1) {                                     // combine the row groups in group order
+        if (rg < rgs) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { red[(rg * cgs + cg) * 8 + i] = S[i]; red[(rg * cgs + cg) * 8 + 4 + i] = Q[i]; }
+        }
+        epi_bar_sync();
+        if (rg == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { S[i] = 0; Q[i] = 0; }
+            for (int g = 0; g < rgs; ++g) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { S[i] += red[(g * cgs + cg) * 8 + i]; Q[i] += red[(g * cgs + cg) * 8 + 4 + i]; }
+            }
+        }
+    }
+    if (rg == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (ep.fin_mode == 1) {
@@ -370,8 +392,8 @@ __device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, i
 }
 // after a CTA's last tile (epilogue warps only): publish its statistics, take a ticket, and finalize if it is the last one
 template <int BN>
-__device__ __forceinline__ void stats_tail(const ConvEpilogue& ep, float* csum, int stat_per_cta, bool has_tiles, int row, int n0, int N,
-                                           int nrows) {
+__device__ __forceinline__ void stats_tail(const ConvEpilogue& ep, float* staging, float* csum, int stat_per_cta, bool has_tiles, int row, int n0,
+                                           int N, int nrows) {
     if (stat_per_cta && has_tiles) flush_cta_stats<BN>(csum, ep.stats, row, n0, N);
     if (!ep.fin_ticket) return;
     __threadfence();                                   // this thread's partial sums are visible device-wide ...
@@ -381,7 +403,7 @@ __device__ __forceinline__ void stats_tail(const ConvEpilogue& ep, float* csum, 
     epi_bar_sync();
     if (*flag) {
         __threadfence();                               // acquire: every other CTA's rows were published before its ticket
-        stats_finalize(ep, nrows, N);
+        stats_finalize(ep, nrows, N, reinterpret_cast<double*>(staging));      // (the staging tile is idle: 18 KB >= 8 KB)
         if (threadIdx.x == 64) *ep.fin_ticket = 0;     // ready for the next launch on this lane
     }
 }
@@ -506,7 +528,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (HAS_STATS)
-            stats_tail<BN>(ep, csum, stat_per_cta, (int)blockIdx.x < total_tiles, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N,
+            stats_tail<BN>(ep, staging, csum, stat_per_cta, (int)blockIdx.x < total_tiles, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N,
                            stat_per_cta ? (int)gridDim.x / n_tiles : m_tiles);
     }
     tc_fence_before();
@@ -691,7 +713,7 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (HAS_STATS)
-            stats_tail<BN>(ep, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
+            stats_tail<BN>(ep, staging, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
                            stat_per_cta ? 2 * (num_clusters / n_tiles) : 2 * m2_tiles);
     }
     tc_fence_before();
@@ -893,7 +915,7 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (HAS_STATS)
-            stats_tail<BN>(ep, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
+            stats_tail<BN>(ep, staging, csum, stat_per_cta, cluster_id < total_tiles, (cluster_id / n_tiles) * 2 + (int)rank, (cluster_id % n_tiles) * BN, N,
                            stat_per_cta ? 2 * (num_clusters / n_tiles) : 2 * m2_tiles);
     }
     tc_fence_before();

@@ -1,6 +1,6 @@
 """One table per kernel CLASS out of an `ncu --set full` report of a forward + backward (tools/one_step.py --mode fwdbwd):
 
-    python tools/ncu_full_table.py gpurun_out/full.ncu-rep [hbm_gbs] > profiles/rN_ncu_full_all_kernels.md
+    python tools/ncu_full_table.py gpurun_out/full.ncu-rep | gpurun_out/raw.csv (= `ncu -i REP --page raw --csv`) [hbm_gbs] > profiles/rN_ncu_all_kernels.md
 
 per class (kernel name incl. template arguments): launches, total / mean duration, DRAM bytes read + written (sum over the launches),
 achieved DRAM GB/s = bytes / duration against the measured copy bandwidth, ncu's DRAM-throughput %, tensor-pipe active %, L2 -> SM
@@ -30,7 +30,7 @@ def main():
     rep = sys.argv[1]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hbm = float(sys.argv[2]) if len(sys.argv) > 2 else json.load(open(os.path.join(root, 'MEASURED_PEAKS.json')))['hbm_gbs']
-    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    txt = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader([ln for ln in txt.splitlines() if ln.startswith('"')]))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {k: hdr.index(v) for k, v in M.items() if v in hdr}

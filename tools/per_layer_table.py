@@ -46,8 +46,9 @@ def terms_of(kernel_name):
     if '<' not in kernel_name:
         return 3
     try:
-        return int(kernel_name[kernel_name.index('<') + 1:kernel_name.rindex('>')].split(',')[-1])
-    except ValueError:
+        args = kernel_name[kernel_name.index('<') + 1:kernel_name.rindex('>')].split(',')
+        return int(args[1] if kernel_name.startswith('conv2w_umma_kernel') else args[-1])      # conv2w_umma_kernel<FL, TERMS, BN>
+    except (ValueError, IndexError):
         return 3
 
 
