@@ -350,9 +350,24 @@ __global__ void __launch_bounds__(256) stem_im2col_rows_kernel(const float* __re
     __shared__ float tile[7 * 102 * IM2COL_MAX_C];
     const int n = blockIdx.y, oy = blockIdx.x;
     const int rowf = 102 * C;                            // floats per staged row
-    for (int i = threadIdx.x; i < 7 * rowf; i += 256) {
-        const int ky = i / rowf, r = i - ky * rowf, px = r / C, c = r - px * C;
-        tile[i] = stem_x(x, layout, C, n, c, 2 * oy + ky - 3, px - 3);
+    if (layout == 0) {                                   // NCHW: generic gather
+        for (int i = threadIdx.x; i < 7 * rowf; i += 256) {
+            const int ky = i / rowf, r = i - ky * rowf, px = r / C, c = r - px * C;
+            tile[i] = stem_x(x, layout, C, n, c, 2 * oy + ky - 3, px - 3);
+        }
+    } else {                                             // NHWC: one thread copies the C contiguous channels of a pixel (no per-element index math)
+        const int pixf = layout == 2 ? C + 1 : C;
+        for (int p = threadIdx.x; p < 7 * 102; p += 256) {
+            const int ky = p / 102, px = p - ky * 102;
+            const int iy = 2 * oy + ky - 3, ix = px - 3;
+            float* dst = tile + ky * rowf + px * C;
+            if (iy < 0 || iy >= 96 || ix < 0 || ix >= 96) {
+                for (int c = 0; c < C; ++c) dst[c] = 0.f;
+            } else {
+                const float* src = x + (((size_t)n * 96 + iy) * 96 + ix) * pixf;
+                for (int c = 0; c < C; ++c) dst[c] = src[c];
+            }
+        }
     }
     __syncthreads();
     const int G = Kp >> 3, NJ = C * 49, run = 7 * C;
