@@ -927,6 +927,184 @@ conv2w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Single-CTA windowed variant for the 3x3 convs of stages 1-2 (N = 64 / 128) on large batches: 128 x BN tiles like conv_umma_kernel,
+// one 184-row activation window per K chunk like conv2w_umma_kernel.  conv_umma_kernel re-loads the 128 A rows for each of the 9 taps,
+// which makes these launches L2-bandwidth-bound (390 / 520 MB of L2 traffic per launch at ~10 TB/s); a CTA PAIR does not help them
+// either, because an SS-mode cta_group::2 MMA with N <= 128 re-reads its A slice from shared memory faster than the 128 B/clk port
+// delivers (measured).  cta_group::1 with N = 128 needs exactly 128 B/clk.  (Round 1 measured "no gain" for this
+// scheme: at that time the issuing thread spent ~54 cycles per MMA, more than a 32-cycle N = 64 MMA takes -- see elect_one.)
+// ------------------------------------------------------------------------------------------------
+template <int TERMS, int BN_>
+struct Conv1WCfg {
+    static constexpr int BN = BN_;
+    static constexpr int A_BYTES = WIN_ROWS * UM_BK * 2;      // one plane of the window (23 KB)
+    static constexpr int W_BYTES = BN * UM_BK * 2;            // one plane of one tap's W tile
+    static constexpr int A_PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int W_PLANES = TERMS >= 2 ? 2 : 1;
+    static constexpr int A_BUF_BYTES = A_PLANES * A_BYTES;
+    static constexpr int W_STAGE_BYTES = W_PLANES * W_BYTES;
+    static constexpr int W_BASE = 2 * A_BUF_BYTES;
+    static constexpr int STAGING_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int CSUM_BYTES = 5 * 2 * BN * 4;
+    static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 + 256;
+    static constexpr int W_FIT = (227 * 1024 - FIXED - W_BASE) / W_STAGE_BYTES;
+    static constexpr int W_STAGES = W_FIT > 6 ? 6 : W_FIT;
+    static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = RING_BYTES + FIXED;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int FL, int TERMS, int BN_>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                   const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int rows, int K,
+                   int N, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
+    using Cfg = Conv1WCfg<TERMS, BN_>;
+    constexpr int BN = Cfg::BN;
+    static_assert(Cfg::A_BYTES % 1024 == 0 && Cfg::W_STAGES >= 2, "window planes must keep the 1024-byte swizzle alignment");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    float* staging = reinterpret_cast<float*>(base_ptr + Cfg::RING_BYTES);
+    float* csum = reinterpret_cast<float*>(base_ptr + Cfg::RING_BYTES + Cfg::STAGING_BYTES);
+    const uint32_t bars = base + Cfg::RING_BYTES + Cfg::STAGING_BYTES + Cfg::CSUM_BYTES;
+    auto afull_bar = [&](int b) { return bars + 8u * b; };
+    auto aempty_bar = [&](int b) { return bars + 8u * (2 + b); };
+    auto wfull_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto wempty_bar = [&](int s) { return bars + 8u * (4 + Cfg::W_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (4 + 2 * Cfg::W_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (6 + 2 * Cfg::W_STAGES + a); };
+    const uint32_t tmem_slot = bars + 8u * (8 + 2 * Cfg::W_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = K / UM_BK;
+    const int total_tiles = m_tiles * n_tiles;
+    const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int steps = my_tiles * kchunks;                  // a "step" g = one (tile, K chunk) = one A window
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(afull_bar(b), 1); mbar_init(aempty_bar(b), 1); }
+        for (int s = 0; s < Cfg::W_STAGES; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mAhi); tma_prefetch_desc(&mAlo); tma_prefetch_desc(&mWhi); tma_prefetch_desc(&mWlo);
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            auto load_window = [&](int g) {        // rows m0 - 26 .. m0 + 157 of K chunk kc (rows outside the tensor are zero-filled)
+                const int tile = (int)blockIdx.x + (g / kchunks) * (int)gridDim.x, kc = g % kchunks;
+                const int m0 = (tile / n_tiles) * UM_BM;
+                const int b = g & 1;
+                mbar_wait(aempty_bar(b), ((uint32_t)(g >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(afull_bar(b), Cfg::A_BUF_BYTES);
+                const uint32_t sa = base + b * Cfg::A_BUF_BYTES;
+                tma_load_2d(sa, &mAhi, afull_bar(b), kc * UM_BK, m0 - WIN_LEAD);
+                if (TERMS == 3) tma_load_2d(sa + Cfg::A_BYTES, &mAlo, afull_bar(b), kc * UM_BK, m0 - WIN_LEAD);
+            };
+            int s = 0; uint32_t ph = 0;
+            if (steps > 0) load_window(0);
+            for (int g = 0; g < steps; ++g) {
+                const int tile = (int)blockIdx.x + (g / kchunks) * (int)gridDim.x, kc = g % kchunks;
+                const int n0 = (tile % n_tiles) * BN;
+                for (int t = 0; t < 9; ++t) {
+                    if (t == 3 && g + 1 < steps) load_window(g + 1);        // prefetch: its buffer was freed a full step ago
+                    mbar_wait(wempty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(wfull_bar(s), Cfg::W_STAGE_BYTES);
+                    const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
+                    tma_load_2d(sw, &mWhi, wfull_bar(s), kc * UM_BK, t * N + n0);
+                    if (TERMS >= 2) tma_load_2d(sw + Cfg::W_BYTES, &mWlo, wfull_bar(s), kc * UM_BK, t * N + n0);
+                    if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {   // warp-wide loop, one elected lane issues (elect_one)
+            constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t aph = 0;
+            for (int g = 0; g < steps; ++g) {
+                const int kc = g % kchunks;
+                if (kc == 0) {
+                    mbar_wait(tempty_bar(acc), aph ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const int b = g & 1;
+                mbar_wait(afull_bar(b), (uint32_t)(g >> 1) & 1u);
+                const uint32_t sa = base + b * Cfg::A_BUF_BYTES;
+                for (int t = 0; t < 9; ++t) {
+                    const int off = (t / 3 - 1) * PITCH + (t % 3 - 1);
+                    const uint32_t arow = sa + (uint32_t)(WIN_LEAD + off) * 128u;
+                    mbar_wait(wfull_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sw = base + Cfg::W_BASE + s * Cfg::W_STAGE_BYTES;
+                    const uint64_t a_hi0 = umma_desc(arow, 16, 1024), w_hi0 = umma_desc(sw, 16, 1024);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < UM_BK / 16; ++k) {
+                            const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
+                            const uint32_t accumulate = (kc | t | k) != 0;
+                            if (TERMS == 3) {
+                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, accumulate);
+                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else if (TERMS == 2) {
+                                const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, accumulate);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                            } else {
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, accumulate);
+                            }
+                        }
+                        tc_commit(wempty_bar(s));
+                        if (t == 8) {
+                            tc_commit(aempty_bar(b));            // the window is free once the 9 taps have read it
+                            if (kc == kchunks - 1) tc_commit(tfull_bar(acc));
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == Cfg::W_STAGES) { s = 0; ph ^= 1u; }
+                }
+                if (kc == kchunks - 1) {
+                    if (++acc == 2) { acc = 0; aph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int acc = 0; uint32_t aph = 0;
+        constexpr bool HAS_STATS = (FL & (EF_STATS | EF_BNBWD)) != 0;
+        const int stat_per_cta = HAS_STATS && gridDim.x % n_tiles == 0;                 // this CTA's tiles share one column block
+        if (stat_per_cta) zero_cta_stats<BN>(csum);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N, out, ep, quad, lane,
+                                         stat_per_cta);
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+        if (HAS_STATS)
+            stats_tail<BN>(ep, staging, csum, stat_per_cta, (int)blockIdx.x < total_tiles, blockIdx.x / n_tiles, ((int)blockIdx.x % n_tiles) * BN, N,
+                           stat_per_cta ? (int)gridDim.x / n_tiles : m_tiles);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad: partial[z][co][ci] = sum_{p in split} dY[p][co] * X[p + off_t][ci],  z = split*ntaps + t
 // ------------------------------------------------------------------------------------------------
 template <int BN, int TERMS = 3>
@@ -1366,13 +1544,43 @@ static int launch_conv2w(const UmmaTensor& A, const UmmaTensor& W, int N, float*
     return 0;
 }
 
+static int small_window_mode() {     // SIMQ_CONV_WINDOW_SMALL=0: stages 1-2 keep the per-tap kernel (A/B experiments)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SIMQ_CONV_WINDOW_SMALL"); mode = e ? atoi(e) : 1; }
+    return mode;
+}
+template <int FL, int TERMS, int BN>
+static int launch_conv1w(const UmmaTensor& A, const UmmaTensor& W, int N, float* out, ConvEpilogue ep, cudaStream_t s) {
+    using Cfg = Conv1WCfg<TERMS, BN>;
+    static unsigned long long attr = 0;      // per-device: function attributes belong to the device context
+    if (first_use_on_device(attr)) SIMQ_CUDA(cudaFuncSetAttribute(conv1w_umma_kernel<FL, TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    const int g_num_sms = num_sms();
+    if (A.rows >= (1LL << 31) - 256) { simq_set_error("k_conv_umma: too many rows"); return 1; }
+    CUtensorMap mAhi, mAlo, mWhi, mWlo;
+    if (make_map(&mAhi, A.t.hi, A.rows, A.cols, WIN_ROWS) || make_map(&mAlo, A.t.lo, A.rows, A.cols, WIN_ROWS) ||
+        make_map(&mWhi, W.t.hi, W.rows, W.cols, BN) || make_map(&mWlo, W.t.lo, W.rows, W.cols, BN))
+        return 1;
+    const int m_tiles = ceil_div(A.rows, UM_BM), n_tiles = N / BN;
+    const int grid = m_tiles * n_tiles < g_num_sms ? m_tiles * n_tiles : g_num_sms;
+    if (ep.stat_rows_out) *ep.stat_rows_out = grid % n_tiles == 0 ? grid / n_tiles : m_tiles;      // see epilogue_tile
+    const double valid_rows = ep.pitch25 ? (double)A.rows * 576.0 / 625.0 : (double)A.rows;
+    prof_mark(PROF_CONV, true, 2.0 * valid_rows * N * A.cols * 9, s, 2.0 * TERMS * (double)A.rows * N * A.cols * 9);
+    conv1w_umma_kernel<FL, TERMS, BN><<<grid, UM_THREADS, Cfg::SMEM_BYTES, s>>>(mAhi, mAlo, mWhi, mWlo, (int)A.rows, A.cols, N, m_tiles, n_tiles, out, ep);
+    prof_mark(PROF_CONV, false, 0, s);
+    SIMQ_LAUNCH_CHECK();
+    return 0;
+}
+
 // the epilogue variants the network uses
-// PAIR: 0 = single-CTA 128 x BN tiles; 1 = CTA-pair 256 x 256 tiles (windowed for 3x3)
+// PAIR: 0 = single-CTA 128 x BN tiles; 1 = CTA-pair 256 x 256 tiles (windowed for 3x3); 2 = single-CTA 128 x BN tiles with the
+// activation window (3x3 only, large batches)
 template <int BN, int PAIR, int F, int TERMS>
 static int conv_launch_t(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, float* out, ConvEpilogue ep, cudaStream_t s) {
     if constexpr (PAIR == 1) {
         if (ntaps == 9 && conv_window_mode() != 0) return launch_conv2w<F, TERMS>(A, W, N, out, ep, s);
         return launch_conv2<F, TERMS>(A, W, N, ntaps, out, ep, s);
+    } else if constexpr (PAIR == 2) {
+        return launch_conv1w<F, TERMS, BN>(A, W, N, out, ep, s);
     } else {
         return launch_conv<BN, F, TERMS>(A, W, N, ntaps, out, ep, s);
     }
@@ -1477,6 +1685,10 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
     // -67 %, but SS-mode MMAs re-read the 128 x 16 A slice from shared memory for every instruction, 6 KB per 32 tensor cycles at
     // N = 128 and 5 KB per 16 at N = 64 against 128 B/clk of shared-memory bandwidth, so the launches got SLOWER (67 vs 50 us, 41 vs
     // 39 us) and the step did not move: dropped.  DESIGN.md section 9.)
+    // stages 1-2 (N = 64 / 128), 3x3, at least one tile per SM: the single-CTA kernel with the activation window
+    if (ntaps == 9 && (N == 64 || N == 128) && policy != 1 && conv_window_mode() != 0 && small_window_mode() != 0 &&
+        ceil_div(A.rows, UM_BM) >= num_sms())
+        return N == 128 ? dispatch_conv<128, 2>(A, W, N, ntaps, out, ep, s) : dispatch_conv<64, 2>(A, W, N, ntaps, out, ep, s);
     if (N % 128 == 0) return dispatch_conv<128>(A, W, N, ntaps, out, ep, s);
     return dispatch_conv<64>(A, W, N, ntaps, out, ep, s);
 }
