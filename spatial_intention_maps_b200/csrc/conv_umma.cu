@@ -341,6 +341,19 @@ __device__ __noinline__ void stats_finalize(const ConvEpilogue& ep, int nrows, i
     double S[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
     if (rg < rgs) {
         int r = rg;
+        for (; r + 15 * rgs < nrows; r += 16 * rgs) {          // 32 float4 loads in flight per thread: the wide layers are latency-bound here
+            float4 a[16], q[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                a[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u * rgs) * 2 + 0) * N + c0));
+                q[u] = __ldcg(reinterpret_cast<const float4*>(st + ((size_t)(r + u * rgs) * 2 + 1) * N + c0));
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                S[0] += a[u].x; S[1] += a[u].y; S[2] += a[u].z; S[3] += a[u].w;
+                Q[0] += q[u].x; Q[1] += q[u].y; Q[2] += q[u].z; Q[3] += q[u].w;
+            }
+        }
         for (; r + 7 * rgs < nrows; r += 8 * rgs) {
             float4 a[8], q[8];
 #pragma unroll
