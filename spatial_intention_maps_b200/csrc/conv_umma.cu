@@ -748,8 +748,7 @@ conv2_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 // the result, leaving it 0 is exact for all 9 row shifts).  The loop order becomes K chunk outer, tap inner; W tiles stream
 // through their own ring.  L2 -> shared traffic per tensor cycle drops from 64 KB to 32 + 47/9 = 37 KB per stage
 // (-42 %): the step is power-bound, fewer bytes moved per MMA = more clock for the MMAs.
-// (The same scheme for the single-CTA 128 x 64/128 tiles of stages 1-2 was built and measured: no gain -- those launches
-// are bound by their epilogues and fixed costs, not by the A loads -- and dropped.)
+// (The single-CTA 128 x 64/128 tiles of stages 1-2 use the same scheme since round 2: conv1w_umma_kernel below.)
 // ------------------------------------------------------------------------------------------------
 
 #define WIN_LEAD 26                                           // PITCH + 1: window row of tile row 0 at tap offset 0
@@ -1693,11 +1692,8 @@ int k_conv_umma(const UmmaTensor& A, const UmmaTensor& W, int N, int ntaps, floa
         const double cost_pair = (double)((t256 + g_num_sms / 2 - 1) / (g_num_sms / 2)) * 2.0 * 0.88;
         if (policy == 3 || (policy == 0 && cost_pair < cost_single)) return dispatch_conv<128, 1>(A, W, N, ntaps, out, ep, s);
     }
-    // (The windowed pair kernel with 256 x 128 / 256 x 64 tiles was built for the 3x3 convs of stages 1-2 -- whose per-tap A loads
-    // make the single-CTA kernel L2-bandwidth-bound, 390 / 520 MB of L2 traffic per launch at ~10 TB/s -- and measured: L2 traffic
-    // -67 %, but SS-mode MMAs re-read the 128 x 16 A slice from shared memory for every instruction, 6 KB per 32 tensor cycles at
-    // N = 128 and 5 KB per 16 at N = 64 against 128 B/clk of shared-memory bandwidth, so the launches got SLOWER (67 vs 50 us, 41 vs
-    // 39 us) and the step did not move: dropped.  DESIGN.md section 9.)
+    // (A windowed PAIR kernel with 256 x 128 / 256 x 64 tiles was built for these layers first and dropped: an SS-mode cta_group::2 MMA
+    // with N <= 128 re-reads its A slice from shared memory faster than the port delivers.  DESIGN.md section 9.)
     // stages 1-2 (N = 64 / 128), 3x3, at least one tile per SM: the single-CTA kernel with the activation window
     if (ntaps == 9 && (N == 64 || N == 128) && policy != 1 && conv_window_mode() != 0 && small_window_mode() != 0 &&
         ceil_div(A.rows, UM_BM) >= num_sms())

@@ -47,7 +47,7 @@ def terms_of(kernel_name):
         return 3
     try:
         args = kernel_name[kernel_name.index('<') + 1:kernel_name.rindex('>')].split(',')
-        return int(args[1] if kernel_name.startswith('conv2w_umma_kernel') else args[-1])      # conv2w_umma_kernel<FL, TERMS, BN>
+        return int(args[1] if kernel_name.startswith(('conv2w_umma_kernel', 'conv1w_umma_kernel')) else args[-1])      # conv{1,2}w_umma_kernel<FL, TERMS, BN>
     except (ValueError, IndexError):
         return 3
 
