@@ -485,13 +485,19 @@ static int wgrad_any(simq_ctx* c, int backend, Split dY, Split X, long long rows
     return k_wgrad_fma(dY, X, rows, Cout, Cin, ntaps, dW, L.scratch, L.s);
 }
 
-static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version, cudaStream_t s, int* err) {
+// keep: a parameter vector whose packed slot must survive this call (the policy's, while the target's weights are looked up: a NEW
+// target pointer -- a freshly built target network -- must take the other slot, not evict the policy's)
+static PackedSet* get_packed(simq_ctx* c, const float* params, uint64_t version, cudaStream_t s, int* err, const float* keep = nullptr) {
     *err = 0;
     PackedSet* ps = nullptr;
     for (int i = 0; i < 2; ++i)
         if (c->packed[i].used && c->packed[i].key == params) ps = &c->packed[i];
     if (ps && version != 0 && ps->version == version) return ps;
-    if (!ps) { ps = &c->packed[c->packed_next]; c->packed_next ^= 1; ++c->pack_epoch; }
+    if (!ps) {
+        int victim = c->packed_next;
+        if (keep && c->packed[victim].used && c->packed[victim].key == keep) victim ^= 1;
+        ps = &c->packed[victim]; c->packed_next = victim ^ 1; ++c->pack_epoch;
+    }
     if (k_pack_all(params, ps->table, ps->n_table, ps->table_total, s)) { *err = 1; return nullptr; }
     if (k_pack_stem(params + c->d.poff[c->d.stem.w], c->d.C, stem_kp(c->d.C), ps->stem, s)) { *err = 1; return nullptr; }
     ps->key = params; ps->version = version; ps->used = true;
@@ -906,7 +912,7 @@ static int train_step_body(simq_ctx* c, float* params, float* bn, int64_t* nbt, 
     if (err) return 1;
     PackedSet* pt = nullptr;
     if (Bn > 0) {
-        pt = get_packed(c, target_params, target_version, s, &err);
+        pt = get_packed(c, target_params, target_version, s, &err, params);
         if (err) return 1;
         pw = nullptr;
         for (int i = 0; i < 2; ++i)

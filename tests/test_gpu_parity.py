@@ -627,3 +627,22 @@ def test_free_running_trajectory_b128_drift_is_bounded():
     assert max(drift) < 1e-1 and max(tdd) < 1e-1
     assert max(r['param_rel_l2'].values()) < 5e-2
     assert r['nbt'] == r['nbt_ref']
+
+
+def test_new_target_network_does_not_evict_the_policy_weights():
+    """The library keeps two packed-weight slots per context.  Swapping in freshly built target networks (new parameter pointers) step
+    after step must never evict the POLICY's slot in the middle of a step (round 1 raised a one-off 'packed policy weights evicted')."""
+    from spatial_intention_maps_b200 import networks, synth, train as T
+    net, st = G.make_net(4, 2, 71, max_batch=4)
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    batch = synth.synth_batch(4, 4, 2, 72, terminal_every=4)
+    losses = []
+    for k in range(5):
+        tgt = networks.FCN(4, 2, max_batch=4)                # a NEW target object (new flat vectors) every step
+        tgt.load_state_dict(st)
+        tgt = tgt.to(G.DEV).eval()
+        with torch.no_grad():
+            net.eval(); net(torch.from_numpy(synth.synth_states(1, 4, k)).to(G.DEV).permute(0, 3, 1, 2)); net.train()   # policy.step between updates
+        losses.append(T.train(G.Cfg(4, 4), net, tgt, opt, batch, None, 0.75)['loss'])
+    assert all(np.isfinite(losses)) and len(set(losses)) > 1
