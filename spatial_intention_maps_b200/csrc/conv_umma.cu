@@ -97,6 +97,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// v = columns [taddr, +32) + columns [taddr + stride, +32): the two partial accumulators of an N-stacked MMA (see Conv1WCfg::STACK);
+// both loads are in flight before the one wait
+__device__ __forceinline__ void tmem_ld32_sum2(uint32_t taddr, uint32_t stride, float* v) {
+    uint32_t r[32], q[32];
+#define SIMQ_LD32(R, ADDR)                                                                                                      \
+    asm volatile(                                                                                                               \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                               \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                               \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                               \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]),           \
+          "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]),                \
+          "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]),               \
+          "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                             \
+        : "r"(ADDR)                                                                                                             \
+        : "memory")
+    SIMQ_LD32(r, taddr);
+    SIMQ_LD32(q, taddr + stride);
+#undef SIMQ_LD32
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+}
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
@@ -161,7 +183,9 @@ struct ConvCfg {
     static constexpr int FIXED = STAGING_BYTES + CSUM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
-    static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
+    static constexpr bool STACK = TERMS >= 2;                 // a.hi * [w.hi ; w.lo] as ONE N = 2 BN instruction, see Conv1WCfg::STACK
+    static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;            // double-buffered accumulator
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -180,7 +204,7 @@ enum { EF_STATS = 1, EF_AFFINE = 2, EF_PREV = 4, EF_RES = 8, EF_G = 16, EF_RELU 
 // fixed tile order = deterministic) and written ONCE per CTA by flush_cta_stats: the finalize / reduce kernel that follows reads
 // <= 148 partial rows instead of one per m-tile (625 at batch 128); 0 -> one partial row per m-tile (CTAs whose tiles span several
 // column blocks).
-template <int BN, int FL, bool CLUSTER>
+template <int BN, int FL, bool CLUSTER, bool STACK = false>
 __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint32_t tmem_acc, uint32_t tempty, int m_t, int n0,
                                               int rows, int N, float* __restrict__ out, const ConvEpilogue& ep, int quad, int lane,
                                               int stat_per_cta) {
@@ -194,7 +218,8 @@ __device__ __forceinline__ void epilogue_tile(float* staging, float* csum, uint3
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
         float v[32];
-        tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+        if (STACK) tmem_ld32_sum2(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, (uint32_t)BN, v);
+        else tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
         if (c + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -487,12 +512,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
     } else if (warp == 1) {
         {   // the whole warp walks the loop (every lane waits on the barriers), one elected lane issues: see elect_one()
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
+            constexpr uint32_t idesc2 = umma_idesc(UM_BM, 2 * BN, 0, 0);      // [W.hi ; W.lo] as one B operand
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
             for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
                 mbar_wait(tempty_bar(acc), aph ^ 1u);           // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
@@ -504,14 +530,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
                             if (TERMS == 3) {
-                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
-                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, (it | k) != 0);
-                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
-                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc2, (it | k) != 0);    // a.hi * [w.hi ; w.lo]: the first one zeroes both halves
+                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, 1);                 // a.lo * w.hi into the first half
                             } else if (TERMS == 2) {
-                                const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
-                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, (it | k) != 0);
-                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc2, (it | k) != 0);
                             } else {
                                 tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, (it | k) != 0);
                             }
@@ -536,8 +559,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
-            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N,
-                                         out + (size_t)z * rows * N, ep, quad, lane, stat_per_cta);
+            epilogue_tile<BN, FL, false, Cfg::STACK>(staging, csum, tmem_base + (uint32_t)(acc * Cfg::ACC_COLS), tempty_bar(acc), m_t, n0, rows, N,
+                                                     out + (size_t)z * rows * N, ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (HAS_STATS)
@@ -963,7 +986,14 @@ struct Conv1WCfg {
     static constexpr int W_STAGES = W_FIT > 6 ? 6 : W_FIT;
     static constexpr int RING_BYTES = W_BASE + W_STAGES * W_STAGE_BYTES;
     static constexpr int SMEM_BYTES = RING_BYTES + FIXED;
-    static constexpr int TMEM_COLS = 2 * BN;
+    // N-STACKED terms: the hi and lo planes of a W tile are adjacent in shared memory with the same 8-row group stride, so ONE
+    // descriptor with N = 2 BN multiplies the A slice with [W.hi ; W.lo] -- a.hi*w.hi lands in accumulator columns [0, BN),
+    // a.hi*w.lo in [BN, 2 BN) -- and the epilogue adds the two halves.  Same three products as before in 2 instructions instead
+    // of 3 (1 instead of 2 at TERMS = 2), and the 128-row A slice -- the operand a narrow-N SS-mode MMA is starved by, see
+    // profiles/r2_ncu_source_conv1w_n64.md -- is read from shared memory twice per product instead of three times.
+    static constexpr bool STACK = TERMS >= 2;
+    static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;            // double-buffered
 };
 
 template <int FL, int TERMS, int BN_>
@@ -973,7 +1003,8 @@ conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                    int N, int m_tiles, int n_tiles, float* __restrict__ out, ConvEpilogue ep) {
     using Cfg = Conv1WCfg<TERMS, BN_>;
     constexpr int BN = Cfg::BN;
-    static_assert(Cfg::A_BYTES % 1024 == 0 && Cfg::W_STAGES >= 2, "window planes must keep the 1024-byte swizzle alignment");
+    static_assert(Cfg::A_BYTES % 1024 == 0 && Cfg::W_BYTES % 1024 == 0 && Cfg::W_STAGES >= 2, "planes must keep the 1024-byte swizzle alignment");
+    static_assert(Cfg::TMEM_COLS <= 512, "two accumulators must fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -1039,6 +1070,7 @@ conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
     } else if (warp == 1) {
         {   // warp-wide loop, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 0, 0);
+            constexpr uint32_t idesc2 = umma_idesc(UM_BM, 2 * BN, 0, 0);      // [W.hi ; W.lo] as one B operand
             int s = 0; uint32_t ph = 0;
             int acc = 0; uint32_t aph = 0;
             for (int g = 0; g < steps; ++g) {
@@ -1047,7 +1079,7 @@ conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                     mbar_wait(tempty_bar(acc), aph ^ 1u);
                     tc_fence_after();
                 }
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
                 const int b = g & 1;
                 mbar_wait(afull_bar(b), (uint32_t)(g >> 1) & 1u);
                 const uint32_t sa = base + b * Cfg::A_BUF_BYTES;
@@ -1064,14 +1096,11 @@ conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
                             const uint64_t a_hi = a_hi0 + (uint64_t)(k * 2), w_hi = w_hi0 + (uint64_t)(k * 2);
                             const uint32_t accumulate = (kc | t | k) != 0;
                             if (TERMS == 3) {
-                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
-                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, accumulate);
-                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, 1);
-                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                                const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc2, accumulate);       // a.hi * [w.hi ; w.lo]: zeroes both halves on the first
+                                tc_mma_bf16(d_tmem, a_lo, w_hi, idesc, 1);                 // a.lo * w.hi into the first half
                             } else if (TERMS == 2) {
-                                const uint64_t w_lo = w_hi + (uint64_t)(Cfg::W_BYTES >> 4);
-                                tc_mma_bf16(d_tmem, a_hi, w_lo, idesc, accumulate);
-                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, 1);
+                                tc_mma_bf16(d_tmem, a_hi, w_hi, idesc2, accumulate);
                             } else {
                                 tc_mma_bf16(d_tmem, a_hi, w_hi, idesc, accumulate);
                             }
@@ -1100,8 +1129,8 @@ conv1w_umma_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_consta
             const int m_t = tile / n_tiles, n0 = (tile - m_t * n_tiles) * BN;
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
-            epilogue_tile<BN, FL, false>(staging, csum, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc), m_t, n0, rows, N, out, ep, quad, lane,
-                                         stat_per_cta);
+            epilogue_tile<BN, FL, false, Cfg::STACK>(staging, csum, tmem_base + (uint32_t)(acc * Cfg::ACC_COLS), tempty_bar(acc), m_t, n0, rows, N, out,
+                                                     ep, quad, lane, stat_per_cta);
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (HAS_STATS)
@@ -1129,6 +1158,10 @@ struct WgradCfg {
     static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + B_PLANES * B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    // single-CTA kernel only: dY.hi * [X.hi | X.lo] as ONE N = 2 BN instruction (the lo plane's 64-channel blocks follow the hi
+    // plane's at the same 8 KB stride); the epilogue adds the two accumulator halves.  See Conv1WCfg::STACK.
+    static constexpr bool STACK = TERMS >= 2 && BN <= 128;
+    static constexpr int ACC_COLS = STACK ? 2 * BN : BN;
 };
 
 template <int BN, int TERMS>
@@ -1160,7 +1193,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&mYhi); tma_prefetch_desc(&mYlo); tma_prefetch_desc(&mXhi); tma_prefetch_desc(&mXlo);
     }
-    if (warp == 1) tmem_alloc<tmem_cols(BN)>(tmem_slot);
+    if (warp == 1) tmem_alloc<tmem_cols(Cfg::ACC_COLS)>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1191,6 +1224,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
     } else if (warp == 1) {
         {   // warp-wide loop, one elected lane issues (elect_one)
             constexpr uint32_t idesc = umma_idesc(UM_BM, BN, 1, 1);
+            constexpr uint32_t idesc2 = umma_idesc(UM_BM, 2 * BN <= 256 ? 2 * BN : BN, 1, 1);      // [X.hi | X.lo] as one B operand
             int s = 0; uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(full_bar(s), ph);
@@ -1203,7 +1237,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < UM_BK / 16; ++k) {
                         const uint64_t y_hi = y_hi0 + (uint64_t)(k * 128), x_hi = x_hi0 + (uint64_t)(k * 128);
-                        if (TERMS == 3) {
+                        if (TERMS == 3 && Cfg::STACK) {
+                            const uint64_t y_lo = y_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+                            tc_mma_bf16(tmem_base, y_hi, x_hi, idesc2, (it | k) != 0);     // the first one zeroes both halves
+                            tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, 1);
+                        } else if (TERMS == 2 && Cfg::STACK) {
+                            tc_mma_bf16(tmem_base, y_hi, x_hi, idesc2, (it | k) != 0);
+                        } else if (TERMS == 3) {
                             const uint64_t y_lo = y_hi + (uint64_t)(Cfg::A_BYTES >> 4), x_lo = x_hi + (uint64_t)(Cfg::B_BYTES >> 4);
                             tc_mma_bf16(tmem_base, y_lo, x_hi, idesc, (it | k) != 0);
                             tc_mma_bf16(tmem_base, y_hi, x_lo, idesc, 1);
@@ -1235,7 +1275,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
         for (int c = 0; c < BN; c += 32) {
             float v[32];
             if (iters > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+                if (Cfg::STACK) tmem_ld32_sum2(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, (uint32_t)BN, v);
+                else tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -1251,7 +1292,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mYhi, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<tmem_cols(BN)>(tmem_base);
+        tmem_dealloc<tmem_cols(Cfg::ACC_COLS)>(tmem_base);
     }
 }
 
