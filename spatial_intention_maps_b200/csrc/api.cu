@@ -155,8 +155,8 @@ struct simq_ctx {
     Split dyA, dyB, dy2h, dy0s; float *stem_tmp, *h2_tmp;
     // second lane (see "lanes" below): its own column-sum partials and split-K / wgrad scratch, the ping-pong partner of
     // dyA, and the stash of the deferred running-statistics update of the s' pass
-    float *partials2, *wscratch2, *wscratch3; Split dyA2; double* bn_defer;
-    cudaStream_t aux_stream, aux2_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[4];
+    float *partials2, *wscratch2, *wscratch3; Split dyA2, dyA3; double* bn_defer;
+    cudaStream_t aux_stream, aux2_stream; cudaEvent_t ev_pool[32]; int ev_next; cudaEvent_t ev_done[5];
     int lanes_mode;                  // -1: read SIMQ_LANES on first use; 0 serial schedule; 1 two lanes
     cudaEvent_t next_ready;          // one-shot (simq_set_next_state_event): the next train step's s' passes wait for it
     float *q_s, *q_no, *q_nt, *dq, *per_sample; long long* best;
@@ -275,6 +275,7 @@ static void carve_all(simq_ctx* c, bool dry) {
     c->stem_partials = carve<float>(c, stem_wgrad_partial_floats(d.C), dry);
     c->dyA = carve_split(c, R25 * 512, dry);
     c->dyA2 = carve_split(c, R25 * 512, dry);
+    c->dyA3 = carve_split(c, R25 * 512, dry);
     c->dyB = carve_split(c, R25 * 512, dry);
     c->dy2h = carve_split(c, R48 * HEAD2_DY_STRIDE, dry);
     c->h2_tmp = carve<float>(c, (size_t)HEAD2_DY_STRIDE * 128, dry);
@@ -433,10 +434,28 @@ static bool lanes_enabled(simq_ctx* c) {
     if (c->lanes_mode < 0) { const char* e = getenv("SIMQ_LANES"); c->lanes_mode = e ? (atoi(e) != 0) : 1; }
     return c->lanes_mode == 1 && !g_prof_on;
 }
+static bool main_priority_enabled() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SIMQ_MAIN_PRIORITY"); mode = e ? (atoi(e) != 0) : 1; }
+    return mode != 0;
+}
+// priority of a side lane: `steps_below_main` levels under the greatest priority, clamped to the device's range
+// (SIMQ_PRIO_AUX / SIMQ_PRIO_AUX2 override the level for experiments)
+static int lane_priority(const char* env, int steps_below_main) {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+    const char* e = getenv(env);
+    if (e) steps_below_main = atoi(e);
+    const int p = greatest + steps_below_main;         // numerically larger = lower priority
+    return p > least ? least : p;
+}
 static int lanes_init(simq_ctx* c) {
     if (c->aux_stream) return 0;
-    SIMQ_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-    SIMQ_CUDA(cudaStreamCreateWithFlags(&c->aux2_stream, cudaStreamNonBlocking));
+    // lane B / W (the online s' pass, then the weight gradients) below the main lane, lane C (target pass: BatchNorm folded, no
+    // elementwise gaps of its own) below that: the lane that is left running alone at the end of the forward phase is the one
+    // without gaps
+    SIMQ_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, main_priority_enabled() ? lane_priority("SIMQ_PRIO_AUX", 2) : 0));
+    SIMQ_CUDA(cudaStreamCreateWithPriority(&c->aux2_stream, cudaStreamNonBlocking, main_priority_enabled() ? lane_priority("SIMQ_PRIO_AUX2", 5) : 0));
     for (auto& e : c->ev_pool) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_done) SIMQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
@@ -689,8 +708,8 @@ static int bias_grad(simq_ctx* c, Split dy, long long rows, int ch, float* out, 
 
 // The backward pass.  Lane M (the caller's stream) runs the chain that carries the gradient from layer to layer --
 // BatchNorm backward (-> dy of the conv below it) and the dgrad GEMMs; every weight-gradient GEMM only needs that dy and a
-// saved activation, so it is handed to lane W.  The dy operand buffers are the hand-over points: dyA ping-pongs with dyA2
-// (lane M may fill the next dy while lane W still reads the previous one), and before any dy buffer is rewritten lane M
+// saved activation, so it is handed to lane W.  The dy operand buffers are the hand-over points: a ring of three (dyA, dyA2, dyA3:
+// lane M may fill the next two dy tensors while lane W still reads an earlier one), and before any dy buffer is rewritten lane M
 // waits for the weight gradient that last read it (ev_done).  Lane W is joined before returning.
 // phase 0: the whole backward.  phase 1: head + layer 4 (after it -- lane W joined -- every gradient from
 // resnet18.layer4.0.conv1.weight to the end of the flat vector is final: 75 % of the bytes, which a data-parallel caller can
@@ -708,9 +727,10 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     TRY(side_stream_for(c, s, &ws));
     const Lane M = main_lane(c, s), W = side_lane(c, ws);
     const bool two = ws != s;
-    enum { BUF_A0 = 0, BUF_A1 = 1, BUF_B = 2, BUF_MISC = 3 };
-    bool pending[4] = {false, false, false, false};
-    Split dyA[2] = {c->dyA, two ? c->dyA2 : c->dyA};
+    enum { BUF_A0 = 0, BUF_A1 = 1, BUF_A2 = 2, BUF_B = 3, BUF_MISC = 4 };
+    bool pending[5] = {false, false, false, false, false};
+    // a ring of THREE: with two, lane M stalls on a weight gradient that lane W (lower priority) has not finished reading
+    Split dyA[3] = {c->dyA, two ? c->dyA2 : c->dyA, two ? c->dyA3 : c->dyA};
     int cur = 1;                                         // index of the dyA buffer written last
     // lane M is about to overwrite dy buffer `buf`: wait for the weight gradient that read it
     auto acquire = [&](int buf) -> int {
@@ -773,7 +793,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     TRY(conv_any(c, be, c->dy2h, R48, HEAD2_DY_STRIDE, pw->bwd[conv_slot(d, d.h2.w)], 128, 1, c->du1, ep0, M, c->terms));
     // ---- head: upsample adjoint, BN1 + conv1 ----
     TRY(k_up1_adj(c->du1, B, G, s));
-    cur ^= 1; TRY(acquire(cur));
+    cur = (cur + 1) % 3; TRY(acquire(cur));
     TRY(bn_backward(c, S, d.hbn1, G, R25, cnt24, 2, nullptr, S.raw_h1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr, none, 0, M));
     TRY(wgrad_on_w(cur, dyA[cur], S.blk[7].out, R25, 128, 512, 1, grads + d.poff[d.h1.w]));
     TRY(bias_grad(c, dyA[cur], R25, 128, grads + d.poff[d.h1_bias], M));
@@ -795,7 +815,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         // every consumer of this block's dy tensors (two dgrads, two or three wgrads) reads the hi plane only: skip the lo planes
         const int hi_only = (be == SIMQ_BACKEND_UMMA && dterms == 2 && c->terms_wgrad == 2) ? 1 : 0;
         // out = relu(bn2(raw2) + identity): dz = G * [out > 0]
-        cur ^= 1; TRY(acquire(cur));
+        cur = (cur + 1) % 3; TRY(acquire(cur));
         if (P.has_ds) TRY(acquire(BUF_B));
         TRY(bn_backward(c, S, P.b2, G, R25, cnt24, 1, Ab.out.hi, Ab.raw2, params, grads, 1, dyA[cur], nullptr, P.has_ds ? &P.bds : nullptr,
                         P.has_ds ? Ab.rawd : nullptr, P.has_ds ? c->dyB : none, P.has_ds ? 0 : g_parts, M, hi_only));
@@ -804,7 +824,7 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
         ConvEpilogue em = with_bn_sums(ep25, P.b1, Ab.raw1, Ab.b1.hi, P.planes, P.planes);
         TRY(conv_any(c, be, dyA[cur], R25, P.planes, pw->bwd[s2], P.planes, 9, c->g_mid, em, M, dterms));
         // b1 = relu(bn1(raw1))
-        cur ^= 1; TRY(acquire(cur));
+        cur = (cur + 1) % 3; TRY(acquire(cur));
         TRY(bn_backward(c, S, P.b1, c->g_mid, R25, cnt24, 1, Ab.b1.hi, Ab.raw1, params, grads, 1, dyA[cur], nullptr, nullptr, nullptr,
                         none, parts_of(em), M, hi_only));
         TRY(wgrad_on_w(cur, dyA[cur], in, R25, P.planes, P.cin, 9, grads + d.poff[P.c1.w]));
@@ -845,6 +865,27 @@ static int run_backward(simq_ctx* c, PackedSet* pw, const float* params, const f
     return 0;
 }
 
+// the internal main-lane stream (greatest priority, see run_graphed) ordered after what `s` holds so far
+static int main_stream_enter(simq_ctx* c, cudaStream_t s, bool prio, cudaStream_t* cs) {
+    if (!c->side_stream) {
+        int least = 0, greatest = 0;
+        SIMQ_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SIMQ_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio ? greatest : least));
+        SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+        SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+    }
+    *cs = c->side_stream;
+    SIMQ_CUDA(cudaEventRecord(c->ev_in, s));
+    SIMQ_CUDA(cudaStreamWaitEvent(*cs, c->ev_in, 0));
+    return 0;
+}
+// ... and `s` ordered after what the main-lane stream has done
+static int main_stream_leave(simq_ctx* c, cudaStream_t s) {
+    SIMQ_CUDA(cudaEventRecord(c->ev_out, c->side_stream));
+    SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
+    return 0;
+}
+
 extern "C" int simq_fcn_backward(simq_ctx* c, const float* params, const float* x, int x_layout, const float* dq, int B,
                                  float* grads, simq_stream stream) {
     if (!c || !params || !x || !dq || !grads) { simq_set_error("simq_fcn_backward: NULL argument"); return 1; }
@@ -854,6 +895,12 @@ extern "C" int simq_fcn_backward(simq_ctx* c, const float* params, const float* 
     for (int i = 0; i < 2; ++i)
         if (c->packed[i].used && c->packed[i].key == params) pw = &c->packed[i];
     if (!pw) { simq_set_error("simq_fcn_backward: parameters were not seen by a forward"); return 1; }
+    if (main_priority_enabled() && lanes_enabled(c)) {        // the weight-gradient lane must not outrank this one
+        cudaStream_t cs;
+        TRY(main_stream_enter(c, s, true, &cs));
+        TRY(run_backward(c, pw, params, x, x_layout, dq, B, grads, cs));
+        return main_stream_leave(c, s);
+    }
     return run_backward(c, pw, params, x, x_layout, dq, B, grads, s);
 }
 
@@ -984,26 +1031,25 @@ static inline uint64_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u;
 template <typename Body, typename OnReplay>
 static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, Body body, OnReplay on_replay) {
     if (c->graph_mode < 0) { const char* e = getenv("SIMQ_GRAPH"); c->graph_mode = e ? (atoi(e) != 0) : 1; }
-    if (!c->graph_mode || g_prof_on || !c->step_warm) {
-        int rc = body(s);
+    // Lane priorities (SIMQ_MAIN_PRIORITY=0 turns them off): the step runs on an internal stream of the greatest priority, the
+    // side lanes keep lower ones (lanes_init), and the graph is instantiated with per-node priorities.  When an input-gradient
+    // convolution of the critical chain and a weight-gradient GEMM are both ready, the SMs go to the convolution and the GEMM
+    // fills in behind it -- under the BatchNorm backward that follows, where the tensor cores used to idle (tools/timeline.py)
+    // -- instead of the two time-slicing the SMs.
+    const bool prio = main_priority_enabled() && lanes_enabled(c);
+    const bool eager = !c->graph_mode || g_prof_on || !c->step_warm;
+    // the legacy default stream cannot be captured: run on a side stream ordered after / before it by events
+    const bool side = prio || (!eager && (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread));
+    cudaStream_t cs = s;
+    if (side) TRY(main_stream_enter(c, s, prio, &cs));
+    if (eager) {
+        int rc = body(cs);
         if (!rc) c->step_warm = true;
+        if (side && !rc) TRY(main_stream_leave(c, s));
         return rc;
     }
     key.push_back((uint64_t)c->backend);
     key.push_back(c->pack_epoch);
-    // the legacy default stream cannot be captured: run on a side stream ordered after / before it by events
-    cudaStream_t cs = s;
-    const bool side = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
-    if (side) {
-        if (!c->side_stream) {
-            SIMQ_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-            SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
-            SIMQ_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
-        }
-        cs = c->side_stream;
-        SIMQ_CUDA(cudaEventRecord(c->ev_in, s));
-        SIMQ_CUDA(cudaStreamWaitEvent(cs, c->ev_in, 0));
-    }
     simq_ctx::GraphEntry* ge = nullptr;
     for (auto& g : c->graphs)
         if (g.key == key) ge = &g;
@@ -1011,10 +1057,7 @@ static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, B
     else if (++c->graph_misses > 16) {                          // never replays: stop paying for capture + instantiate
         c->graph_mode = 0;
         int rc = body(cs);
-        if (side && !rc) {
-            SIMQ_CUDA(cudaEventRecord(c->ev_out, cs));
-            SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
-        }
+        if (side && !rc) TRY(main_stream_leave(c, s));
         return rc;
     }
     if (!ge) {
@@ -1032,7 +1075,7 @@ static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, B
             return 1;
         }
         cudaGraphExec_t exec = nullptr;
-        e = cudaGraphInstantiate(&exec, graph, 0);
+        e = cudaGraphInstantiateWithFlags(&exec, graph, prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { simq_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return 1; }
         if (c->graphs.size() >= 8) {                            // evict the least recently used
@@ -1050,10 +1093,7 @@ static int run_graphed(simq_ctx* c, std::vector<uint64_t> key, cudaStream_t s, B
     on_replay();                                                // host-side bookkeeping the eager body would have done
     SIMQ_CUDA(cudaGraphLaunch(ge->exec, cs));
     g_simq_launches += ge->launches;
-    if (side) {
-        SIMQ_CUDA(cudaEventRecord(c->ev_out, cs));
-        SIMQ_CUDA(cudaStreamWaitEvent(s, c->ev_out, 0));
-    }
+    if (side) TRY(main_stream_leave(c, s));
     return 0;
 }
 
