@@ -293,3 +293,52 @@ def test_mark_params_changed_bumps_the_version_data_writes_do_not():
     assert net.params_version == v0
     net.mark_params_changed()
     assert net.params_version > v0
+
+
+BENCH_LINES = ['r2_final_bench.json', 'r2_final_bench_n2.json', 'r2_final_bench_n4.json', 'r2_final_bench_n8.json']
+
+
+@pytest.mark.parametrize('name', BENCH_LINES)
+def test_committed_bench_lines_follow_the_contract(name):
+    """The bench lines kept under profiles/ are what DESIGN.md quotes: each must be ONE JSON line with the driver contract's keys,
+    internally consistent (value = samples per step / time, roofline.frac = achieved / peak, e2e with its copy sizes), measured with
+    clocks the contract accepts, and -- at N > 1 -- carry a passed multi-rank parity check."""
+    import json
+    path = os.path.join(ROOT, 'profiles', name)
+    text = open(path).read().strip()
+    assert '\n' not in text, 'one JSON line'
+    d = json.loads(text)
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype',
+              'data', 'config', 'e2e', 'gpu_launches', 'roofline', 'clocks'):
+        assert k in d, k
+    assert d['unit'] == 'samples/s' and d['higher_is_better'] is True and d['scaling'] == 'weak' and d['data'] == 'synthetic'
+    assert d['vs_baseline'] is None                                  # BASELINE.md has no published number for this metric
+    assert d['warmup'] >= 3 and d['steps'] >= 1 and d['gpu_launches'] > 0
+    n = d['n_gpus']
+    assert d['config']['global_batch'] == 128 * n and 'workload' in d['config'] and 'model' not in d['config']
+    assert abs(d['value'] - d['config']['global_batch'] / d['ms_per_step'] * 1e3) <= 1e-6 * d['value']
+    r = d['roofline']
+    assert r['bound'] in ('hbm', 'tensor') and r['unit'] in ('GB/s', 'TFLOP/s')
+    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9 and 0.0 < r['frac'] < 1.0
+    assert r['issued_frac'] < 1.4                                    # issued MMAs against the sustained peak: plausibility bound
+    e = d['e2e']
+    assert e['unit'] == d['unit'] and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0
+    assert e['value'] <= d['value'] * 1.02                           # the end-to-end number cannot beat the device-resident one
+    bad = {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    assert not bad & set(d['clocks']['reasons'])
+    if n == 1:
+        cb = d['cpu_baseline']
+        assert cb['kind'] == 'reference' and cb['cores'] >= 1 and cb['value'] > 0 and 'sample' in cb
+        assert cb['argmax_check_vs_cpu_oracle']['eval_argmax_equal'] == cb['argmax_check_vs_cpu_oracle']['samples']
+    else:
+        assert d['config']['parity_check']['ok'] is True
+
+
+def test_committed_reference_arm_line():
+    import json
+    d = json.loads(open(os.path.join(ROOT, 'profiles', 'r2_final_bench_reference_arm.json')).read().strip())
+    mine = json.loads(open(os.path.join(ROOT, 'profiles', 'r2_final_bench.json')).read().strip())
+    assert d['impl'] == 'reference' and d['metric'] == mine['metric'] and d['unit'] == mine['unit']
+    assert d['config']['workload'] == mine['config']['workload'] and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'reference' and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
