@@ -268,37 +268,50 @@ int k_stem_pool(const float* raw0, int B, const float* scale, const float* shift
 }
 
 // head: BN1 + ReLU + bilinear x2 (24->48, align_corners) : raw_h1 pitch-25 [.,128] -> u1 split dense
+// One block = one output row (n, oy): the two source rows it interpolates between (24 pixels x 128 channels each, contiguous in
+// the pitch-25 layout) are staged in shared memory with BN + ReLU applied once, by coalesced float4 loads; then a thread produces
+// 8 channels of 3 output pixels from shared memory.  (The first version gathered 4 x 32 bytes per thread from global memory and
+// re-applied BN + ReLU per tap: 0.28 of the copy bandwidth, 100 us per launch at batch 128.)
 __global__ void __launch_bounds__(256) head_up1_kernel(const float* __restrict__ raw, int B,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        Split u1) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * 2304 * 16;
-    if (idx >= total) return;
-    long long pos = idx >> 4;
-    int c = (int)(idx & 15) * 8;
-    int n = (int)(pos / 2304), r = (int)(pos % 2304), oy = r / 48, ox = r % 48;
-    int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+    __shared__ __align__(16) float src[2][24 * 128];
+    const int n = blockIdx.x / 48, oy = blockIdx.x % 48;
+    int y0, y1; float wy0, wy1;
     bilin_src(oy, 24, 48, y0, y1, wy0, wy1);
-    bilin_src(ox, 24, 48, x0, x1, wx0, wx1);
-    float sc[8], sh[8], v00[8], v01[8], v10[8], v11[8], o[8];
-    load8(scale + c, sc); load8(shift + c, sh);
-    const float* base = raw + (size_t)n * IMG25 * 128 + c;
-    load8(base + (size_t)(y0 * PITCH + x0) * 128, v00);
-    load8(base + (size_t)(y0 * PITCH + x1) * 128, v01);
-    load8(base + (size_t)(y1 * PITCH + x0) * 128, v10);
-    load8(base + (size_t)(y1 * PITCH + x1) * 128, v11);
+    {
+        const int c4 = (threadIdx.x & 31) * 4;                    // channel group of this thread: the same for all its loads
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c4), sh = *reinterpret_cast<const float4*>(shift + c4);
+        const float* base = raw + (size_t)n * IMG25 * 128;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float a = fmaxf(fmaf(v00[i], sc[i], sh[i]), 0.f), b = fmaxf(fmaf(v01[i], sc[i], sh[i]), 0.f);
-        float cc = fmaxf(fmaf(v10[i], sc[i], sh[i]), 0.f), d = fmaxf(fmaf(v11[i], sc[i], sh[i]), 0.f);
-        o[i] = wy0 * (wx0 * a + wx1 * b) + wy1 * (wx0 * cc + wx1 * d);
+        for (int k = 0; k < 6; ++k) {                             // 2 rows x 24 pixels x 32 float4 = 1536 = 6 x 256
+            const int i = k * 256 + threadIdx.x;
+            const int r = i / 768, px = (i % 768) >> 5;
+            const float4 v = *reinterpret_cast<const float4*>(base + (size_t)((r ? y1 : y0) * PITCH + px) * 128 + c4);
+            float4 o;
+            o.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+            o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+            *reinterpret_cast<float4*>(&src[r][px * 128 + c4]) = o;
+        }
     }
-    store8_split(u1, (size_t)pos * 128 + c, o);
+    __syncthreads();
+    const int c = (threadIdx.x & 15) * 8;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ox = k * 16 + (threadIdx.x >> 4);
+        int x0, x1; float wx0, wx1;
+        bilin_src(ox, 24, 48, x0, x1, wx0, wx1);
+        float v00[8], v01[8], v10[8], v11[8], o[8];
+        load8(&src[0][x0 * 128 + c], v00); load8(&src[0][x1 * 128 + c], v01);
+        load8(&src[1][x0 * 128 + c], v10); load8(&src[1][x1 * 128 + c], v11);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = wy0 * (wx0 * v00[i] + wx1 * v01[i]) + wy1 * (wx0 * v10[i] + wx1 * v11[i]);
+        store8_split(u1, ((size_t)(n * 48 + oy) * 48 + ox) * 128 + c, o);
+    }
 }
 
 int k_head_up1(const float* raw_h1, int B, const float* scale, const float* shift, Split u1, cudaStream_t s) {
-    long long n = (long long)B * 2304 * 16;
-    head_up1_kernel<<<grid_for(n, 256), 256, 0, s>>>(raw_h1, B, scale, shift, u1);
+    head_up1_kernel<<<B * 48, 256, 0, s>>>(raw_h1, B, scale, shift, u1);
     SIMQ_LAUNCH_CHECK();
     return 0;
 }
