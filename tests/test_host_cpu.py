@@ -342,3 +342,22 @@ def test_committed_reference_arm_line():
     assert d['config']['workload'] == mine['config']['workload'] and d['higher_is_better'] is True
     assert d['cpu_baseline']['kind'] == 'reference' and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_timeline_tool_reproduces_the_committed_analysis():
+    """profiles/r2_timeline.md quotes tools/timeline.py's analysis of the committed kernel timeline: re-derive it from the CSV."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('timeline_tool', os.path.join(ROOT, 'tools', 'timeline.py'))
+    tl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tl)
+    r = tl.analyse(tl.load_csv(os.path.join(ROOT, 'profiles', 'r2_timeline_after.csv')))
+    assert r['kernels'] == 243                                           # the launches of one step
+    assert abs(r['span'] / 1e3 - 19.59) < 0.02 and abs(r['tensor_idle'] / 1e3 - 1.30) < 0.02
+    assert r['tensor_sum'] > r['tensor_union'] > 0                       # tensor-core kernels of different lanes overlap
+    assert r['no_kernel'] < 0.05e3                                       # the graph leaves no launch gaps
+    text = open(os.path.join(ROOT, 'profiles', 'r2_timeline.md')).read()
+    assert tl.report(r).splitlines()[0] in text
+    # a synthetic case: two tensor kernels with an elementwise kernel between them
+    s = tl.analyse([(0.0, 10.0, 'conv_umma_kernel<64, 65, 3>'), (10.0, 14.0, 'bn_apply_kernel<0>'), (15.0, 25.0, 'wgrad_umma_kernel<64, 2>')])
+    assert s['span'] == 25.0 and s['tensor_union'] == 20.0 and s['tensor_idle'] == 5.0 and abs(s['no_kernel'] - 1.0) < 1e-9
+    assert dict(s['fill']) == {'bn_apply_kernel<0>': 4.0}

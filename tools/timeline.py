@@ -1,6 +1,7 @@
 """Kernel timeline of ONE train step in its real (multi-lane, graphed) schedule, from CUPTI through torch.profiler:
 
-    python tools/timeline.py [--batch 128] [--graph 1] --out gpurun_out/timeline.csv
+    python tools/timeline.py [--batch 128] --out gpurun_out/timeline.csv        # on a GPU box (SIMQ_GRAPH=0 for eager launches)
+    python tools/timeline.py --csv profiles/r2_timeline_after.csv               # re-analyse a committed timeline, no GPU
 
 Writes one row per kernel (name, stream, start us, duration us) and prints where the step's time goes: the union of the
 intervals in which a tensor-core kernel is running, the rest ("tensor-idle" time), and which kernels fill the idle gaps.
@@ -13,10 +14,6 @@ import re
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch  # noqa: E402
-
-import bench  # noqa: E402
-from spatial_intention_maps_b200 import networks, synth, train as T  # noqa: E402
 
 TENSOR = re.compile(r'(conv\w*_umma_kernel|wgrad\w*_umma_kernel)')
 
@@ -25,12 +22,85 @@ def short(name):
     return re.sub(r'\(.*', '', name).replace('void ', '')
 
 
+def analyse(ev):
+    """ev: (start us, end us, kernel name) of every kernel of one step.  Returns the step span, the union of the intervals in
+    which a tensor-core kernel runs, the tensor-idle time, how much of it has no kernel at all, what fills the rest, and the gaps."""
+    ev = sorted(ev)
+    t0 = ev[0][0]
+    span = max(e for _, e, _ in ev) - t0
+    tens = sorted((s, e) for s, e, n in ev if TENSOR.search(n))
+    merged = []
+    for s, e in tens:
+        if merged and s <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], e)
+        else:
+            merged.append([s, e])
+    busy = sum(e - s for s, e in merged)
+    gaps = []
+    prev = t0
+    for s, e in merged:
+        if s > prev:
+            gaps.append((prev, s))
+        prev = max(prev, e)
+    if prev < t0 + span:
+        gaps.append((prev, t0 + span))
+    fill = collections.Counter()
+    empty = 0.0
+    for gs, ge in gaps:
+        covered = []
+        for s, e, n in ev:
+            if TENSOR.search(n) or e <= gs or s >= ge:
+                continue
+            lo, hi = max(s, gs), min(e, ge)
+            fill[n] += hi - lo
+            covered.append((lo, hi))
+        covered.sort()
+        c = 0.0
+        p = gs
+        for lo, hi in covered:
+            if hi > p:
+                c += hi - max(lo, p)
+                p = hi
+        empty += (ge - gs) - c
+    return {'t0': t0, 'span': span, 'kernels': len(ev), 'tensor_sum': sum(e - s for s, e in tens), 'tensor_union': busy,
+            'tensor_idle': span - busy, 'no_kernel': empty, 'fill': fill, 'gaps': gaps, 'ev': ev}
+
+
+def report(r):
+    out = [f"step span {r['span'] / 1e3:.2f} ms, {r['kernels']} kernels; tensor-core kernels: sum of durations {r['tensor_sum'] / 1e3:.2f} ms, "
+           f"union {r['tensor_union'] / 1e3:.2f} ms; tensor-idle {r['tensor_idle'] / 1e3:.2f} ms",
+           f"{len(r['gaps'])} gaps; {r['no_kernel'] / 1e3:.2f} ms of them with NO kernel running at all (launch / dependency latency)",
+           '| kernel running while no tensor-core kernel runs | us |', '|---|---|']
+    for n, v in r['fill'].most_common(25):
+        out.append(f'| `{n}` | {v:.0f} |')
+    out.append('largest gaps (start us, length us, tensor kernel before -> after):')
+    big = sorted(r['gaps'], key=lambda g: g[0] - g[1])[:15]
+    for gs, ge in sorted(big):
+        before = [n for s, e, n in r['ev'] if TENSOR.search(n) and abs(e - gs) < 0.5]
+        after = [n for s, e, n in r['ev'] if TENSOR.search(n) and abs(s - ge) < 0.5]
+        out.append(f"  {gs - r['t0']:9.1f} {ge - gs:7.1f}  {before[:1]} -> {after[:1]}")
+    return '\n'.join(out)
+
+
+def load_csv(path):
+    """rows written by main(): start_us, dur_us, kernel"""
+    with open(path, newline='') as f:
+        return [(float(r['start_us']), float(r['start_us']) + float(r['dur_us']), r['kernel']) for r in csv.DictReader(f)]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=128)
     ap.add_argument('--warm', type=int, default=6)
     ap.add_argument('--out', default='gpurun_out/timeline.csv')
+    ap.add_argument('--csv', default=None, help='re-analyse a timeline written earlier (no GPU needed)')
     a = ap.parse_args()
+    if a.csv:
+        print(report(analyse(load_csv(a.csv))))
+        return
+    import torch
+    import bench
+    from spatial_intention_maps_b200 import networks, synth, train as T
     dev = torch.device('cuda', 0)
     B = a.batch
     pol, tgt, opt = bench.make_nets(networks, torch, dev, bench.C_IN, bench.A_OUT, B)
@@ -67,57 +137,8 @@ def main():
         w.writerow(['start_us', 'dur_us', 'kernel'])
         for s, e, n, _ in ev:
             w.writerow([f'{s - t0:.1f}', f'{e - s:.1f}', n])
-    span = max(e for _, e, _, _ in ev) - t0
-    # union of tensor-kernel intervals
-    tens = sorted((s, e) for s, e, n, _ in ev if TENSOR.search(n))
-    merged = []
-    for s, e in tens:
-        if merged and s <= merged[-1][1]:
-            merged[-1][1] = max(merged[-1][1], e)
-        else:
-            merged.append([s, e])
-    busy = sum(e - s for s, e in merged)
-    tens_sum = sum(e - s for s, e in tens)
-    print(f'step span {span / 1e3:.2f} ms, {len(ev)} kernels; tensor-core kernels: sum of durations {tens_sum / 1e3:.2f} ms, union {busy / 1e3:.2f} ms; '
-          f'tensor-idle {(span - busy) / 1e3:.2f} ms')
-    # gaps and what runs in them
-    gaps = []
-    prev = t0
-    for s, e in merged:
-        if s > prev:
-            gaps.append((prev, s))
-        prev = max(prev, e)
-    if prev < t0 + span:
-        gaps.append((prev, t0 + span))
-    fill = collections.Counter()
-    empty = 0.0
-    for gs, ge in gaps:
-        covered = []
-        for s, e, n, _ in ev:
-            if TENSOR.search(n) or e <= gs or s >= ge:
-                continue
-            lo, hi = max(s, gs), min(e, ge)
-            fill[n] += hi - lo
-            covered.append((lo, hi))
-        covered.sort()
-        c = 0.0
-        p = gs
-        for lo, hi in covered:
-            if hi > p:
-                c += hi - max(lo, p)
-                p = hi
-        empty += (ge - gs) - c
-    print(f'{len(gaps)} gaps; {empty / 1e3:.2f} ms of them with NO kernel running at all (launch / dependency latency)')
-    print('| kernel running while no tensor-core kernel runs | us |')
-    print('|---|---|')
-    for n, v in fill.most_common(25):
-        print(f'| `{n}` | {v:.0f} |')
-    big = sorted(gaps, key=lambda g: g[0] - g[1])[:15]
-    print('largest gaps (start us, length us, tensor kernel before -> after):')
-    for gs, ge in sorted(big):
-        before = [n for s, e, n, _ in ev if TENSOR.search(n) and abs(e - gs) < 0.5]
-        after = [n for s, e, n, _ in ev if TENSOR.search(n) and abs(s - ge) < 0.5]
-        print(f'  {gs - t0:9.1f} {ge - gs:7.1f}  {before[:1]} -> {after[:1]}')
+    rep = analyse([(s_, e_, n_) for s_, e_, n_, _ in ev])
+    print(report(rep))
 
 
 if __name__ == '__main__':
